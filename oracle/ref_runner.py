@@ -1,0 +1,61 @@
+"""Import the UNMODIFIED reference from /root/reference  --  TEST INFRASTRUCTURE ONLY.
+
+Works only in the authoring container (the GPU box has no /root/reference).  Four stub packages
+under ``oracle/_stubs`` stand in for the reference's missing imports (xarray, dask, utm,
+yaconfigobject).  Used by ``oracle/make_golden.py`` to generate the golden
+vectors in ``tests/golden`` and by ``tests/test_oracle.py`` (skipped when the reference is absent).
+"""
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+REFERENCE_ROOT = "/root/reference"
+_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_stubs")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "topo_descriptors"))
+
+
+def load():
+    """Return (topo, helpers) modules of the reference."""
+    if not available():
+        raise RuntimeError("reference tree not present")
+    for p in (REFERENCE_ROOT, _STUBS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import topo_descriptors.helpers as hlp
+        import topo_descriptors.topo as topo
+    return topo, hlp
+
+
+def fake_dataset(z, x, y, crs="epsg:2056", name="alti"):
+    """Duck-typed Dataset subclassing the stub ``xarray.Dataset`` so the reference's isinstance
+    checks pass (topo.py:825, helpers.py:179)."""
+    load()
+    import xarray as xr  # the stub
+
+    class _DA:
+        def __init__(self, values, dims):
+            self.values = values
+            self.dims = dims
+            self.data = values
+
+    class _DS(xr.Dataset):
+        def __init__(self):
+            self.attrs = {"crs": crs}
+            self._v = {name: _DA(z, ("y", "x")), "x": _DA(np.asarray(x), ("x",)), "y": _DA(np.asarray(y), ("y",))}
+            self.coords = {"x": self._v["x"], "y": self._v["y"]}
+
+        def __iter__(self):
+            return iter([name])
+
+        def __getitem__(self, key):
+            return self._v[key]
+
+    return _DS()
