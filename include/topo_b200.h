@@ -1,0 +1,149 @@
+/*
+ * topo_b200.h  --  C ABI of libtopo_b200.so, the sm_100a implementation of the raster-filter hot
+ * path of MeteoSwiss/topo-descriptors.
+ *
+ * The reference has no FFI: its boundary is the Python function API of topo_descriptors/topo.py.
+ * Each entry point below replaces the *array kernel* behind one of those functions; the host shim
+ * (topo_descriptors_b200/topo.py) keeps the reference signatures and calls these through ctypes.
+ * Citations are reference file:line (topo.py = topo_descriptors/topo.py).
+ *
+ * Conventions
+ *  - All image pointers are DEVICE pointers to row-major float32 rasters; `ld*` = row pitch in
+ *    elements.  Nothing here allocates: scratch is passed in (`ws`, size from the *_workspace_bytes
+ *    twin).  Launches are asynchronous on `stream` (a cudaStream_t passed as void*).
+ *  - Return value: 0 = ok, < 0 = error; topo_last_error() returns a thread-local message.  Nothing
+ *    throws across the ABI.
+ *  - Row bands (multi-GPU sharding): every stencil takes a *view*.  The input
+ *    buffer holds global rows [in_gy0, in_gy0+in_rows) of an image that is `gny` rows tall; the
+ *    call writes global rows [out_gy0, out_gy0+out_rows) to `out` (row 0 of `out` = out_gy0).
+ *    Border rules (zero padding / reflect / one-sided differences / the Sx frame) are always
+ *    applied in GLOBAL coordinates, so a band + halo gives bit-identical pixels to the full image.
+ *    The caller guarantees the input band covers every in-image row the stencil touches.
+ *    Whole image on one GPU: in_gy0 = out_gy0 = 0, in_rows = out_rows = gny.
+ */
+#ifndef TOPO_B200_H
+#define TOPO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct topo_view {
+    int nx;       /* columns */
+    int gny;      /* rows of the GLOBAL image */
+    int in_gy0;   /* global row of input row 0 */
+    int in_rows;  /* rows present in the input buffer */
+    int out_gy0;  /* global row of output row 0 */
+    int out_rows; /* rows to compute */
+} topo_view;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int topo_version(void);
+const char* topo_last_error(void);
+/* Number of kernel launches issued through this library by the calling process (bench.py's
+ * `gpu_launches` claim). */
+long long topo_launch_count(void);
+/* Per-kernel timing for bench.py: while enabled, every launch is bracketed by CUDA events on its
+ * stream.  topo_profile_dump synchronises on them, writes "<kernel> <launches> <total_ms> <max_ms>"
+ * lines into buf and clears the records. */
+int topo_profile_enable(int on);
+int topo_profile_dump(char* buf, size_t cap);
+
+/* ---- DEM statistics (one pass, cached by the host per uploaded DEM) ------------------------ */
+/* out_stats (DEVICE, 8 doubles): [0] min [1] max [2] #non-finite [3] #non-integer-valued
+ * [4] sum [5] sum of squares [6] n [7] reserved.  Deterministic two-stage reduction.
+ * Feeds: the fixed-point scale of the disc sums, the all-NaN rule of the FFT-based reference
+ * functions (topo.py:175,301-302,443), and valley_ridge's global z-score (topo.py:429). */
+size_t topo_dem_stats_workspace_bytes(int rows, int nx);
+int topo_dem_stats_f32(const float* dem, int rows, int nx, int64_t ld, double* out_stats, void* ws,
+                       size_t ws_bytes, void* stream);
+
+/* out[i] = value (NaN re-stamp of whole outputs, the reference's FFT behaviour on NaN input). */
+int topo_fill_f32(float* out, int rows, int nx, int64_t ld, float value, void* stream);
+/* out[rows[i], cols[i]] = value : `array[ind_nans] = np.nan` of the compute_* drivers
+ * (topo.py:57,139,267,385,591), on device. */
+int topo_stamp_f32(float* out, int64_t ld, const int* rows, const int* cols, int64_t n, float value,
+                   void* stream);
+
+/* ---- TPI (topo.py:144-181) and STD (topo.py:272-307): disc sums ------------------------------
+ * Zero-padded "same" convolution with circular_kernel(size) (topo.py:191-213; a square for
+ * size < 5), scipy centring for even sizes.  Per-row prefix sums in 32-bit fixed point
+ * (wrap-around arithmetic, so every span difference is exact) + one span difference per kernel
+ * row, accumulated in 64-bit integers; float64 epilogue.
+ *   TPI: out = dem - (disc_sum - excluded_centre) / (N - 1)
+ *   STD: out = sqrt(max((sum trunc(x)^2 - (sum x)^2 / N) / (N - 1), 0))      (float32 result; the
+ *        host up-casts to float64 like the reference).  trunc(x) reproduces
+ *        `dem.astype("int32") ** 2` (topo.py:300): the squares use the truncated elevation.
+ * zmin/zmax: GLOBAL finite range of the DEM (from topo_dem_stats_f32); all_integer: 1 if every
+ * value is integral (enables the 2-array exact path for STD).
+ * Small/medium sizes run fused (tile + halo prefix in shared memory); large sizes run two passes
+ * through `ws`. */
+size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi, 1 std*/);
+int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
+                 int size, double zmin, double zmax, void* ws, size_t ws_bytes, void* stream);
+int topo_std_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
+                 int size, int all_integer, double zmin, double zmax, void* ws,
+                 size_t ws_bytes, void* stream);
+
+/* ---- Gaussian smoothing (topo.py:62-80; scipy.ndimage.gaussian_filter semantics) -------------
+ * Separable, radius int(4*sigma+0.5), float64 weights and accumulation, axis 0 then axis 1 with a
+ * float32 round in between, reflect borders (d c b a | a b c d | d c b a) in global coordinates.
+ * w_y / w_x: DEVICE arrays of lw+1 float64 half-kernels (w[0] = centre tap) computed by the host
+ * exactly as scipy's _gaussian_kernel1d does; a null pointer skips that axis (sigma <= 1e-15).
+ * `ws` holds the axis-0 result. */
+size_t topo_gauss_workspace_bytes(const topo_view* v, int lw_y, int lw_x);
+int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
+                   const double* w_y, int lw_y, const double* w_x, int lw_x, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* ---- gradient / slope / aspect (topo.py:597-644, 688-712) -------------------------------------
+ * From smoothed surfaces gx (differentiated along x) and gy (along y; same pointer when
+ * sig_ratio == 1): numpy.gradient central differences (one-sided at the global edges), division
+ * by the signed grid resolution, slope = atan(hypot) in degrees, aspect = (180 + deg(atan2(dx,
+ * dy))) mod 360 -- all in float32 in the reference's operation order.  res_x: (nx) or, if
+ * res_x_2d, (gny, nx) float64 addressed by GLOBAL row; res_y: (gny) or (gny, nx). */
+int topo_grad_from_smooth_f32(const float* gx, const float* gy, int64_t ld_in, float* dx, float* dy,
+                              float* slope, float* aspect, int64_t ld_out, const topo_view* v,
+                              const double* res_x, int res_x_2d, const double* res_y, int res_y_2d,
+                              void* stream);
+/* Sobel branch, sigma <= 1 (topo.py:628-629, 658-685): ndimage.convolve with K/8 and K.T/8,
+ * reflect borders, float64 accumulation; same normalisation / slope / aspect epilogue fused. */
+int topo_sobel_gradient_f32(const float* dem, int64_t ld_in, float* dx, float* dy, float* slope,
+                            float* aspect, int64_t ld_out, const topo_view* v, const double* res_x,
+                            int res_x_2d, const double* res_y, int res_y_2d, int normalize,
+                            void* stream);
+
+/* ---- Sx (topo.py:775-858, 928-953) --------------------------------------------------------------
+ * n_az azimuth sectors in one launch.  offsets: (dy, dx) int pairs of the de-duplicated ray
+ * samples of all sectors, inv_dist: 1/distance per sample (float32), az_begin[n_az+1]: CSR ranges
+ * (all DEVICE arrays).  dy_min/dy_max: extreme row offsets over all samples (band check).
+ * out: [n_az] planes `az_stride` elements apart.  Pixels within `window` of any GLOBAL edge are 0;
+ * NaN samples are skipped, a NaN centre or an empty sample list gives NaN (np.nanmax semantics). */
+int topo_sx_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int64_t az_stride,
+                const topo_view* v, const int* offsets, const float* inv_dist, const int* az_begin,
+                int n_az, int window, float height, int dy_min, int dy_max, void* stream);
+
+/* ---- valley / ridge (topo.py:389-453) ------------------------------------------------------------
+ * z-score with the global mean/std (topo.py:429), then ALL angles in one launch with a running
+ * strict-'>' max and argmax over the angles, norm clipped at 0 (topo.py:441-452).
+ * bank (DEVICE): for angle a, at element offset bank_off[a] (multiple of 4), a [w][hp][4] float32
+ * array: kernel column j, row i, 4 channel slots (n_ch used, rest 0); rows h..hp-1 are zero, hp is
+ * a multiple of 4 and >= h + 3.  The kernels are already channel-mixed (the reference's 3-D
+ * convolution sums neighbouring flat-list kernels, topo.py:431,443) and flipped, so the device
+ * correlates:  out[y,x] = sum Kf[i,j] * d[y + i - h/2, x + j - w/2], zero outside the image.
+ * bank_hw (DEVICE): 4 ints per angle: h, w, hp, 0.  hmax/wmax: maxima of h and w over the angles.
+ * dir receives the angle index (degrees, angles are 0..n_angles-1). */
+int topo_zscore_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int rows, int nx,
+                    float mean, float std, void* stream);
+int topo_valley_ridge_f32(const float* dem_norm, int64_t ld_in, float* norm, float* dir, int64_t ld_out,
+                          const topo_view* v, const float* bank, const int* bank_hw,
+                          const int64_t* bank_off, int n_angles, int n_ch, int hmax, int wmax,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPO_B200_H */

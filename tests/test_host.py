@@ -1,0 +1,223 @@
+"""Host logic of the drop-in boundary (no GPU): helpers, Sx geometry, valley/ridge kernel bank,
+Dataset duck-types, output names, and the C-ABI library's symbol table."""
+
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from topo_descriptors_b200 import CFG, _geometry as geo, _lib, _xr, helpers as hlp, topo
+from topo_descriptors_b200.synth import dem_dataset, fractal_dem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- the reference's own known-answer tests against the new host code (test/test_topo.py, test_helpers.py)
+def test_sx_distance():
+    out = topo._sx_distance(150.0, 50.0, 40.0)
+    expected = np.array([256.1249695, 219.31712199, 188.67962264, 167.63054614, 160.0,
+                         167.63054614, 188.67962264, 219.31712199, 256.1249695])
+    assert np.all(np.isclose(out[0, :], expected))
+    assert out.dtype == np.float64
+
+
+def test_sx_bresenhamlines():
+    out = topo._sx_bresenhamlines(np.array([[8, 9], [17, 22]]), np.array([15, 15]))
+    expected = np.array([[9, 10], [10, 11], [11, 12], [12, 12], [13, 13], [14, 14],
+                         [17, 21], [16, 20], [16, 19], [16, 18], [16, 17], [15, 16]])
+    assert np.all(out == expected)
+    assert out.dtype == np.int64
+
+
+def test_sx_source_idx_delta():
+    out = topo._sx_source_idx_delta(np.array([3.0, 4.0, 5.0, 6.0]), 500, 20, 30)
+    assert np.all(out == np.array([[17, 1], [17, 2], [17, 2], [17, 3]]))
+    assert out.dtype == np.int64
+
+
+def test_round_up_to_odd():
+    out = hlp.round_up_to_odd(np.arange(0.1, 10, 0.7))
+    assert out.dtype == np.int64
+    assert all(a == b for a, b in zip(out, [1, 1, 1, 3, 3, 3, 5, 5, 5, 7, 7, 7, 9, 9, 9]))
+
+
+# ---- golden vectors (reference outputs) --------------------------------------------------------
+def test_helpers_against_golden(golden):
+    z = golden["in__z"]
+    ds = _xr.Dataset({"alti": (("y", "x"), z)}, coords={"x": golden["in__x"], "y": golden["in__y"]},
+                     attrs={"crs": "epsg:2056"})
+    px, res = hlp.scale_to_pixel(list(golden["scale_to_pixel__scales"]), ds)
+    assert px.dtype == np.int64 and np.array_equal(px, golden["scale_to_pixel__px"])
+    assert np.array_equal(res["x"], golden["scale_to_pixel__res_x"])
+    assert np.array_equal(res["y"], golden["scale_to_pixel__res_y"])
+    sig = hlp.get_sigmas([None, 0.5, 0, 1, 2.5], px)
+    want = golden["get_sigmas__out"]
+    for s, w in zip(sig, want):
+        assert (s is None and np.isnan(w)) or s == w
+    assert np.array_equal(hlp.round_up_to_odd(golden["round_up_to_odd__in"]), golden["round_up_to_odd__out"])
+
+
+@pytest.mark.parametrize("size", [3, 4, 5, 6, 7, 17, 33])
+def test_circular_kernel(golden, size):
+    k = topo.circular_kernel(size)
+    assert k.dtype == np.float32 and np.array_equal(k, golden[f"circular_kernel__{size}"])
+
+
+def test_sx_geometry_against_golden(golden):
+    assert np.array_equal(geo.sx_distance(150.0, 30.0, -30.0), golden["sx_distance__150_30_-30"])
+    assert np.array_equal(geo.sx_source_idx_delta(np.linspace(-5, 5, 15), 150.0, 30.0, -30.0),
+                          golden["sx_source_idx_delta__b"])
+    assert np.array_equal(geo.sx_bresenhamlines(np.array([[8, 9], [17, 22]]), np.array([15, 15])),
+                          golden["sx_bresenhamlines__a"])
+
+
+def test_sx_lines_match_oracle_on_random_sectors():
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        radius = float(rng.integers(60, 900))
+        dx = float(rng.choice([20.0, 25.0, 30.0, 50.0]))
+        dy = -float(rng.choice([20.0, 25.0, 30.0, 40.0]))
+        az = float(rng.uniform(0, 360))
+        arc = float(rng.choice([0.0, 10.0, 30.0]))
+        steps = int(rng.integers(1, 20))
+        azs = np.linspace(az - arc / 2, az + arc / 2, 1 if arc == 0 else steps)
+        dist = geo.sx_distance(radius, dx, dy)
+        assert np.array_equal(dist, O.sx_distance(radius, dx, dy))
+        centre = np.floor(np.array(dist.shape) / 2)
+        src = (centre + geo.sx_source_idx_delta(azs, radius, dx, dy)).astype(int)
+        assert np.array_equal(geo.sx_bresenhamlines(src, centre), O.sx_bresenhamlines(src, centre))
+
+
+def test_sx_samples_dedupe_and_mask():
+    dist = geo.sx_distance(150.0, 30.0, -30.0)
+    dist[dist < 60.0] = np.nan
+    centre = np.floor(np.array(dist.shape) / 2)
+    src = (centre + geo.sx_source_idx_delta(np.linspace(40, 50, 15), 150.0, 30.0, -30.0)).astype(int)
+    lines = geo.sx_bresenhamlines(src, centre)
+    off, inv, window = geo.sx_samples(dist, lines)
+    assert window == 5 and off.dtype == np.int32 and inv.dtype == np.float32
+    assert len(np.unique(off, axis=0)) == len(off) <= len(lines)
+    d = np.hypot(off[:, 0] * 30.0, off[:, 1] * 30.0)
+    assert np.all(d >= 60.0) and np.allclose(inv, 1.0 / d, rtol=1e-6)
+
+
+def test_valley_bank(golden):
+    k = geo.valley_kernels(7, [0, 0.15, 0.3])
+    assert k.dtype == np.float32 and np.allclose(k, golden["valley_kernels__7"], atol=1e-6)
+    assert np.allclose(topo._ridge_kernels(7, [0, 0.15, 0.3]), -golden["valley_kernels__7"], atol=1e-6)
+    for ang in (0, 30, 45, 90, 137):
+        got = topo._rotate_kernels(k, np.float32(ang))
+        assert got.dtype == np.float32 and np.allclose(got, golden[f"rotate_kernels__7_{ang}"], atol=2e-6)
+    bank = geo.build_valley_bank(7, "valley", [0, 0.15, 0.3])
+    assert bank["n_angles"] == 180 and bank["n_ch"] == 3
+    for a in (0, 33, 90, 179):
+        h, w, hp, _ = bank["hw"][a]
+        assert hp % 4 == 0 and hp >= h + 3 and bank["off"][a] % 4 == 0
+        blk = bank["data"][bank["off"][a] : bank["off"][a] + w * hp * 4].reshape(w, hp, 4)
+        want = O.valley_ridge_channel_kernels(O.rotate_kernels(O.valley_kernels(7, [0, 0.15, 0.3]), np.float32(a)))
+        got = np.transpose(blk[:, :h, :3], (2, 1, 0))[:, ::-1, ::-1]  # undo flip + layout
+        assert np.allclose(got, want, atol=1e-5)
+        assert not blk[:, h:, :].any() and not blk[:, :, 3].any()
+    with pytest.raises(ValueError):
+        geo.build_valley_bank(7, "gully", [0])
+
+
+def test_output_names(golden):
+    names = [
+        topo._dem_name(200), topo._tpi_name(200, None), topo._tpi_name(2000, 0.5), topo._std_name(200, 1),
+        *topo._valley_ridge_names(1000, "valley", 0.5), *topo._gradient_names(200, 1), *topo._gradient_names(2000, 1.5),
+        topo._sx_name(500.0, 45.0),
+    ]
+    assert names == list(golden["names__all"])
+
+
+# ---- data model ------------------------------------------------------------------------------------
+def test_check_dem_errors():
+    z = np.zeros((4, 5), np.float32)
+    good = dem_dataset(z)
+    hlp.check_dem(good)
+    with pytest.raises(ValueError):
+        hlp.check_dem(z)
+    with pytest.raises(ValueError):
+        hlp.check_dem(_xr.Dataset({"a": (("x", "y"), z)}, attrs={"crs": "epsg:2056"}))
+    with pytest.raises(KeyError):
+        hlp.check_dem(_xr.Dataset({"a": (("y", "x"), z)}, attrs={}))
+    with pytest.raises(ValueError):
+        hlp.check_dem(_xr.Dataset({"a": (("y", "x"), z)}, attrs={"crs": "wgs84"}))
+    with pytest.raises(TypeError):
+        topo.sx(z, 0, 100)
+    with pytest.raises(ValueError):
+        topo.valley_ridge(z, 5, "gully")
+
+
+def test_cfg_defaults():
+    assert CFG.scale_std == 4 and CFG.min_elevation == -100
+
+
+def test_wgs84_resolution():
+    # utm.from_latlon(51.2, 7.5) == (395201.3103811303, 5673135.241182375, 32, 'U')  (utm package docs)
+    e, n = hlp._wgs84_to_utm(51.2, 7.5)
+    assert abs(e - 395201.3103811303) < 1e-3 and abs(n - 5673135.241182375) < 1e-3
+    lon = 8.0 + np.arange(40) / 3600.0
+    lat = 46.5 - np.arange(30) / 3600.0
+    ds = _xr.Dataset({"a": (("y", "x"), np.zeros((30, 40), np.float32))}, coords={"x": lon, "y": lat},
+                     attrs={"crs": "EPSG:4326"})
+    px, res = hlp.scale_to_pixel([500], ds)
+    assert res["x"].shape == (30, 40) and res["y"].shape == (30, 40)
+    assert 20 < res["x"].mean() < 23 and -32 < res["y"].mean() < -30  # 1 arc-second at 46.5 N
+    assert px[0] % 2 == 1
+
+
+def test_fill_na_nearest():
+    z = np.arange(24, dtype=np.float32).reshape(3, 8)
+    z[0, 0:2] = np.nan
+    z[1, 3] = np.nan
+    z[2, 6:] = np.nan
+    ind, filled = hlp.fill_na(dem_dataset(z))
+    assert len(ind[0]) == 5
+    f = hlp.get_da(filled).values
+    assert not np.isnan(f).any()
+    assert f[0, 0] == 2 and f[0, 1] == 2 and f[1, 3] == 10 and f[2, 6] == 21 and f[2, 7] == 21
+
+
+def test_to_netcdf_npz_sink(tmp_path):
+    z = fractal_dem(12, 16, seed=1)
+    ds = dem_dataset(z, res=30.0)
+    x, y = ds["x"].values, ds["y"].values
+    crop = {"x": slice(x[2], x[9]), "y": slice(y[3], y[8])}  # y descends: slice(hi, lo)
+    p = hlp.to_netcdf(z * 2, ds, "tpi_200m", crop, tmp_path, "m")
+    assert p.name == "topo_TPI_200M.npz"
+    with np.load(p) as f:
+        assert f["TPI_200M"].shape == (6, 8) and np.array_equal(f["TPI_200M"], (z * 2)[3:9, 2:10])
+        assert str(f["units"]) == "m" and np.array_equal(f["x"], x[2:10])
+
+
+# ---- the C-ABI library --------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "topo_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(topo_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/topo_b200.h but not exported"
+    assert declared == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+    assert lib.topo_version() >= 100
+    v = _lib.View(1440, 900, 0, 900, 0, 900)
+    import ctypes
+
+    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 17, 0) == 0  # fused: no workspace
+    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 801, 0) > 4 * 900 * 1440
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        topo.tpi(np.zeros((8, 8), np.float32), 3)
+    with pytest.raises(RuntimeError):
+        topo.gradient(np.zeros((8, 8), np.float32), 2.0, {"x": np.ones(8), "y": np.ones(8)})

@@ -1,0 +1,291 @@
+// Library plumbing + the small whole-raster kernels: DEM statistics, fill, NaN re-stamp, z-score.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace topo {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-kernel timing ---------------------------------------------------------------------------
+struct ProfRecord {
+    const char* name;
+    cudaEvent_t start, stop;
+};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRecord> g_prof;
+
+ProfScope::ProfScope(const char* name, cudaStream_t s) : slot(-1), stream(s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRecord r;
+    r.name = name;
+    if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+    cudaEventRecord(r.start, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    slot = (int)g_prof.size();
+    g_prof.push_back(r);
+}
+
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[slot].stop, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DEM statistics: min, max, #non-finite, #non-integer, sum, sum of squares, n.
+// Stage 1: one partial per CTA (fixed assignment of rows to CTAs => deterministic);
+// stage 2: a single CTA folds the partials in index order.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStatsThreads = 256;
+constexpr int kStatsFields = 8;
+
+struct StatsAcc {
+    double mn, mx, nonfinite, nonint, sum, sumsq, n;
+    __device__ void init() {
+        mn = INFINITY;
+        mx = -INFINITY;
+        nonfinite = nonint = sum = sumsq = n = 0.0;
+    }
+    __device__ void add(float z) {
+        if (isfinite(z)) {
+            double d = (double)z;
+            mn = fmin(mn, d);
+            mx = fmax(mx, d);
+            sum += d;
+            sumsq += d * d;
+            if (truncf(z) != z) nonint += 1.0;
+        } else {
+            nonfinite += 1.0;
+        }
+        n += 1.0;
+    }
+    __device__ void merge(const StatsAcc& o) {
+        mn = fmin(mn, o.mn);
+        mx = fmax(mx, o.mx);
+        nonfinite += o.nonfinite;
+        nonint += o.nonint;
+        sum += o.sum;
+        sumsq += o.sumsq;
+        n += o.n;
+    }
+    __device__ void shfl_merge(int d) {
+        StatsAcc o;
+        o.mn = __shfl_down_sync(0xffffffffu, mn, d);
+        o.mx = __shfl_down_sync(0xffffffffu, mx, d);
+        o.nonfinite = __shfl_down_sync(0xffffffffu, nonfinite, d);
+        o.nonint = __shfl_down_sync(0xffffffffu, nonint, d);
+        o.sum = __shfl_down_sync(0xffffffffu, sum, d);
+        o.sumsq = __shfl_down_sync(0xffffffffu, sumsq, d);
+        o.n = __shfl_down_sync(0xffffffffu, n, d);
+        merge(o);
+    }
+};
+
+__device__ void block_reduce_store(StatsAcc a, double* dst) {
+    __shared__ double sm[kStatsThreads / 32][kStatsFields];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a.shfl_merge(d);
+    if (lane == 0) {
+        sm[warp][0] = a.mn, sm[warp][1] = a.mx, sm[warp][2] = a.nonfinite, sm[warp][3] = a.nonint;
+        sm[warp][4] = a.sum, sm[warp][5] = a.sumsq, sm[warp][6] = a.n, sm[warp][7] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        StatsAcc t;
+        t.init();
+        for (int w = 0; w < kStatsThreads / 32; ++w) {
+            StatsAcc o;
+            o.mn = sm[w][0], o.mx = sm[w][1], o.nonfinite = sm[w][2], o.nonint = sm[w][3];
+            o.sum = sm[w][4], o.sumsq = sm[w][5], o.n = sm[w][6];
+            t.merge(o);
+        }
+        dst[0] = t.mn, dst[1] = t.mx, dst[2] = t.nonfinite, dst[3] = t.nonint;
+        dst[4] = t.sum, dst[5] = t.sumsq, dst[6] = t.n, dst[7] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kStatsThreads) stats_partial_kernel(const float* __restrict__ dem,
+                                                                      int rows, int nx, int64_t ld,
+                                                                      double* __restrict__ partials) {
+    StatsAcc a;
+    a.init();
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(dem) & 15) == 0);
+    for (int y = blockIdx.x; y < rows; y += gridDim.x) {
+        const float* row = dem + (int64_t)y * ld;
+        if (vec) {
+            const int nv = nx >> 2;
+            for (int i = threadIdx.x; i < nv; i += kStatsThreads) {
+                float4 v = ldg4(row + 4 * i);
+                a.add(v.x), a.add(v.y), a.add(v.z), a.add(v.w);
+            }
+            for (int x = (nv << 2) + threadIdx.x; x < nx; x += kStatsThreads) a.add(__ldg(row + x));
+        } else {
+            for (int x = threadIdx.x; x < nx; x += kStatsThreads) a.add(__ldg(row + x));
+        }
+    }
+    block_reduce_store(a, partials + (int64_t)blockIdx.x * kStatsFields);
+}
+
+__global__ void __launch_bounds__(kStatsThreads) stats_final_kernel(const double* __restrict__ partials,
+                                                                    int n_partials,
+                                                                    double* __restrict__ out) {
+    // fixed order: thread t folds partials t, t+256, ... ; then the block tree.
+    StatsAcc a;
+    a.init();
+    for (int i = threadIdx.x; i < n_partials; i += kStatsThreads) {
+        const double* p = partials + (int64_t)i * kStatsFields;
+        StatsAcc o;
+        o.mn = p[0], o.mx = p[1], o.nonfinite = p[2], o.nonint = p[3], o.sum = p[4], o.sumsq = p[5],
+        o.n = p[6];
+        a.merge(o);
+    }
+    block_reduce_store(a, out);
+}
+
+static int stats_grid(int rows) {
+    int g = kNumSMs * 4;
+    return rows < g ? rows : g;
+}
+
+__global__ void fill_kernel(float* __restrict__ out, int rows, int nx, int64_t ld, float value) {
+    const int64_t total = (int64_t)rows * nx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int y = (int)(i / nx), x = (int)(i - (int64_t)y * nx);
+        out[(int64_t)y * ld + x] = value;
+    }
+}
+
+__global__ void stamp_kernel(float* __restrict__ out, int64_t ld, const int* __restrict__ rows,
+                             const int* __restrict__ cols, int64_t n, float value) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)rows[i] * ld + cols[i]] = value;
+}
+
+// (dem - mean) / std in float32, exactly the two float32 operations of topo.py:429.
+__global__ void zscore_kernel(const float* __restrict__ in, int64_t ld_in, float* __restrict__ out,
+                              int64_t ld_out, int rows, int nx, float mean, float sd) {
+    const int64_t total = (int64_t)rows * nx;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int y = (int)(i / nx), x = (int)(i - (int64_t)y * nx);
+        out[(int64_t)y * ld_out + x] = __fdiv_rn(__fsub_rn(in[(int64_t)y * ld_in + x], mean), sd);
+    }
+}
+
+static int elementwise_grid(int64_t total, int threads) {
+    int64_t b = ceil_div64(total, threads);
+    int64_t cap = (int64_t)kNumSMs * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace topo
+
+using namespace topo;
+
+extern "C" {
+
+int topo_version(void) { return 100; }
+
+const char* topo_last_error(void) { return g_err; }
+
+long long topo_launch_count(void) { return g_launches.load(); }
+
+int topo_profile_enable(int on) {
+    g_prof_on.store(on ? 1 : 0);
+    return 0;
+}
+
+// Writes one line per kernel name: "<name> <launches> <total_ms> <max_ms>\n"; clears the records.
+int topo_profile_dump(char* buf, size_t cap) {
+    TOPO_CHECK(buf && cap > 0, "null buffer");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    struct Agg { long n = 0; double ms = 0, mx = 0; };
+    std::map<std::string, Agg> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+            Agg& a = agg[r.name];
+            a.n += 1, a.ms += ms;
+            if (ms > a.mx) a.mx = ms;
+        }
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_prof.clear();
+    std::string out;
+    char line[256];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s %ld %.6f %.6f\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.mx);
+        out += line;
+    }
+    TOPO_CHECK(out.size() + 1 <= cap, "profile buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+
+size_t topo_dem_stats_workspace_bytes(int rows, int nx) {
+    (void)nx;
+    return (size_t)stats_grid(rows > 0 ? rows : 1) * kStatsFields * sizeof(double);
+}
+
+int topo_dem_stats_f32(const float* dem, int rows, int nx, int64_t ld, double* out_stats, void* ws,
+                       size_t ws_bytes, void* stream) {
+    TOPO_CHECK(dem && out_stats && ws, "null pointer");
+    TOPO_CHECK(rows > 0 && nx > 0 && ld >= nx, "bad shape %d x %d (ld %lld)", rows, nx, (long long)ld);
+    TOPO_CHECK(ws_bytes >= topo_dem_stats_workspace_bytes(rows, nx), "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int g = stats_grid(rows);
+    TOPO_LAUNCH("stats_partial", s, stats_partial_kernel<<<g, kStatsThreads, 0, s>>>(dem, rows, nx, ld, (double*)ws));
+    TOPO_LAUNCH("stats_final", s, stats_final_kernel<<<1, kStatsThreads, 0, s>>>((const double*)ws, g, out_stats));
+    return 0;
+}
+
+int topo_fill_f32(float* out, int rows, int nx, int64_t ld, float value, void* stream) {
+    TOPO_CHECK(out && rows >= 0 && nx > 0 && ld >= nx, "bad arguments");
+    if (rows == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    TOPO_LAUNCH("fill", s, fill_kernel<<<elementwise_grid((int64_t)rows * nx, 256), 256, 0, s>>>(out, rows, nx, ld, value));
+    return 0;
+}
+
+int topo_stamp_f32(float* out, int64_t ld, const int* rows, const int* cols, int64_t n, float value,
+                   void* stream) {
+    TOPO_CHECK(out && n >= 0, "bad arguments");
+    if (n == 0) return 0;
+    TOPO_CHECK(rows && cols, "null index arrays");
+    cudaStream_t s = (cudaStream_t)stream;
+    TOPO_LAUNCH("stamp", s, stamp_kernel<<<elementwise_grid(n, 256), 256, 0, s>>>(out, ld, rows, cols, n, value));
+    return 0;
+}
+
+int topo_zscore_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int rows, int nx,
+                    float mean, float sd, void* stream) {
+    TOPO_CHECK(dem && out && rows > 0 && nx > 0, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    TOPO_LAUNCH("zscore", s, zscore_kernel<<<elementwise_grid((int64_t)rows * nx, 256), 256, 0, s>>>(dem, ld_in, out, ld_out, rows, nx, mean, sd));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// Gaussian smoothing, gradient / slope / aspect, Sobel.
+// Reference: topo.py:62-80 (dem), 597-644 (gradient), 658-685 (sobel), 688-712 (_normalize_dxy);
+// third-party semantics restated from scipy.ndimage (gaussian_filter -> correlate1d per axis, axis 0
+// first, float64 line buffers and accumulators, output rounded to the input dtype after each axis,
+// mode="reflect") and numpy.gradient (central differences, first-order one-sided at the edges).
+//
+// Separable passes, register-blocked: every thread owns K consecutive outputs ALONG the filter axis and
+// slides over K + 2*lw inputs, keeping a rotating window of K weights in registers, so each loaded
+// sample feeds K float64 FMAs.  Axis 0: lanes = columns (coalesced global loads, neighbouring row
+// groups share lines through L1).  Axis 1: the row segment + halo is staged in shared memory (reflect
+// applied while staging) and lanes = rows with an odd pitch (conflict-free), outputs are transposed
+// back through shared memory for coalesced stores.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace topo {
+
+constexpr int kK = 8;  // outputs per thread along the filter axis
+
+struct GaussParams {
+    const float* in;
+    float* out;
+    int64_t ld_in, ld_out;
+    int nx, gny;
+    int in_gy0, in_rows;    // rows present in `in`
+    int out_gy0, out_rows;  // rows to produce
+    const double* w;        // device: w[0] = centre ... w[lw]
+    int lw;
+};
+
+// weights in shared memory, padded with zeros so that index min(|t|, lw+1) needs no branch
+__device__ __forceinline__ void stage_weights(const GaussParams& p, double* wsm) {
+    for (int i = threadIdx.x + threadIdx.y * blockDim.x; i <= p.lw + 1; i += blockDim.x * blockDim.y)
+        wsm[i] = (i <= p.lw) ? p.w[i] : 0.0;
+}
+
+__device__ __forceinline__ double weight_at(const double* wsm, int t, int lw) {
+    int a = t < 0 ? -t : t;
+    return wsm[a > lw ? lw + 1 : a];
+}
+
+// ---- axis 0 (along y) -----------------------------------------------------------------------------
+// block (32, 8): 32 columns x 8 row groups of K rows.
+__global__ void __launch_bounds__(256) gauss_axis0_kernel(const GaussParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* wsm = reinterpret_cast<double*>(smem_raw);
+    stage_weights(p, wsm);
+    __syncthreads();
+
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int gy0 = p.out_gy0 + (blockIdx.y * 8 + threadIdx.y) * kK;  // first output row of this thread
+    if (gy0 >= p.out_gy0 + p.out_rows) return;                        // warp-uniform
+    const int xc = x < p.nx ? x : p.nx - 1;
+    const int lw = p.lw;
+
+    double acc[kK], wr[kK];
+#pragma unroll
+    for (int k = 0; k < kK; ++k) acc[k] = 0.0, wr[k] = 0.0;
+
+    const int in_end = p.in_gy0 + p.in_rows;
+    for (int t0 = -lw; t0 <= kK - 1 + lw; t0 += kK) {
+#pragma unroll
+        for (int s = 0; s < kK; ++s) {
+            const int t = t0 + s;
+#pragma unroll
+            for (int k = kK - 1; k > 0; --k) wr[k] = wr[k - 1];
+            wr[0] = weight_at(wsm, t, lw);
+            const int g = reflect_index(gy0 + t, p.gny);
+            float v = 0.f;
+            if (g >= p.in_gy0 && g < in_end) v = __ldg(p.in + (int64_t)(g - p.in_gy0) * p.ld_in + xc);
+            const double dv = (double)v;
+#pragma unroll
+            for (int k = 0; k < kK; ++k) acc[k] = fma(wr[k], dv, acc[k]);
+        }
+    }
+    if (x < p.nx) {
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+            const int gy = gy0 + k;
+            if (gy < p.out_gy0 + p.out_rows) p.out[(int64_t)(gy - p.out_gy0) * p.ld_out + x] = (float)acc[k];
+        }
+    }
+}
+
+// ---- axis 1 (along x) -----------------------------------------------------------------------------
+// block 256 = 8 warps.  Tile: TR rows (lanes) x 128 output columns; warp w owns columns
+// [w*8, w*8+8) of each 64-column half.
+constexpr int kA1Cols = 128;
+
+__global__ void __launch_bounds__(256) gauss_axis1_kernel(const GaussParams p, int TR, int pitch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* wsm = reinterpret_cast<double*>(smem_raw);
+    const int wcount = (p.lw + 2 + 1) & ~1;
+    float* tile = reinterpret_cast<float*>(wsm + wcount);       // [TR][pitch]
+    float* otile = tile + (size_t)TR * pitch;                   // [TR][kA1Cols + 1]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lw = p.lw;
+
+    for (int i = threadIdx.x; i <= lw + 1; i += 256) wsm[i] = (i <= lw) ? p.w[i] : 0.0;
+
+    const int x0 = blockIdx.x * kA1Cols;
+    const int r0 = blockIdx.y * TR;  // first row (relative to the output band) of this tile
+    const int span = kA1Cols + 2 * lw;
+    // stage: warp per row, lanes along x, reflect at the global left/right edges
+    for (int r = warp; r < TR; r += 8) {
+        const int row = r0 + r;
+        float* dst = tile + (size_t)r * pitch;
+        if (row < p.out_rows) {
+            const float* src = p.in + (int64_t)(p.out_gy0 + row - p.in_gy0) * p.ld_in;
+            for (int c = lane; c < span; c += 32) dst[c] = __ldg(src + reflect_index(x0 - lw + c, p.nx));
+        } else {
+            for (int c = lane; c < span; c += 32) dst[c] = 0.f;
+        }
+    }
+    __syncthreads();
+
+    if (lane < TR) {
+        const float* trow = tile + (size_t)lane * pitch;
+#pragma unroll 1
+        for (int half = 0; half < kA1Cols / 64; ++half) {
+            const int c0 = half * 64 + warp * kK;  // first output column (tile-relative) of this thread
+            double acc[kK], wr[kK];
+#pragma unroll
+            for (int k = 0; k < kK; ++k) acc[k] = 0.0, wr[k] = 0.0;
+            for (int t0 = -lw; t0 <= kK - 1 + lw; t0 += kK) {
+#pragma unroll
+                for (int s = 0; s < kK; ++s) {
+                    const int t = t0 + s;
+#pragma unroll
+                    for (int k = kK - 1; k > 0; --k) wr[k] = wr[k - 1];
+                    wr[0] = weight_at(wsm, t, lw);
+                    // tile column of input x0 + c0 + t is c0 + t + lw; past the staged span only with
+                    // zero weight
+                    int c = c0 + t + lw;
+                    c = c < span ? c : span - 1;
+                    const double dv = (double)trow[c];
+#pragma unroll
+                    for (int k = 0; k < kK; ++k) acc[k] = fma(wr[k], dv, acc[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kK; ++k) otile[lane * (kA1Cols + 1) + c0 + k] = (float)acc[k];
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < TR; r += 8) {
+        const int row = r0 + r;
+        if (row >= p.out_rows) break;
+        float* dst = p.out + (int64_t)row * p.ld_out;
+        for (int c = lane; c < kA1Cols; c += 32)
+            if (x0 + c < p.nx) dst[x0 + c] = otile[r * (kA1Cols + 1) + c];
+    }
+}
+
+// ---- derivative / slope / aspect epilogue ------------------------------------------------------------
+struct GradParams {
+    const float* gx;  // differentiated along x
+    const float* gy;  // differentiated along y
+    float *dx, *dy, *slope, *aspect;
+    int64_t ld_in, ld_out;
+    int nx, gny, in_gy0, in_rows, out_gy0, out_rows;
+    const double* res_x;
+    const double* res_y;
+    int res_x_2d, res_y_2d, normalize;
+};
+
+__device__ __forceinline__ void finish_gradient(const GradParams& p, float dx, float dy, int gy, int x) {
+    if (p.normalize) {
+        // `dx /= res` with a float64 resolution array: float64 division, rounded back to float32
+        const double rx = p.res_x_2d ? p.res_x[(int64_t)gy * p.nx + x] : p.res_x[x];
+        const double ry = p.res_y_2d ? p.res_y[(int64_t)gy * p.nx + x] : p.res_y[gy];
+        dx = (float)((double)dx / rx);
+        dy = (float)((double)dy / ry);
+    }
+    const int64_t o = (int64_t)(gy - p.out_gy0) * p.ld_out + x;
+    p.dx[o] = dx;
+    p.dy[o] = dy;
+    if (p.slope) {
+        // np.arctan(np.sqrt(dx**2 + dy**2)) * (180 / np.pi), every step in float32
+        const float h2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        p.slope[o] = __fmul_rn(atanf(sqrtf(h2)), 57.29577951308232f);
+    }
+    if (p.aspect) {
+        // (180 + np.degrees(np.arctan2(dx, dy))) % 360 in float32, Python modulo
+        // np.degrees on float32 multiplies by 180.0f / NPY_PIf = 57.2957763671875f (one ulp below
+        // float32(180/pi) used for the slope above)
+        const float deg = __fmul_rn(atan2f(dx, dy), 57.2957763671875f);
+        float a = __fadd_rn(180.0f, deg);
+        a = fmodf(a, 360.0f);
+        if (a < 0.f) a += 360.0f;
+        p.aspect[o] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256) grad_from_smooth_kernel(const GradParams p) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int gy = p.out_gy0 + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= p.nx || gy >= p.out_gy0 + p.out_rows) return;
+    const float* rx = p.gx + (int64_t)(gy - p.in_gy0) * p.ld_in;
+    float dx, dy;
+    if (x == 0)
+        dx = __fsub_rn(__ldg(rx + 1), __ldg(rx));
+    else if (x == p.nx - 1)
+        dx = __fsub_rn(__ldg(rx + x), __ldg(rx + x - 1));
+    else
+        dx = __fdiv_rn(__fsub_rn(__ldg(rx + x + 1), __ldg(rx + x - 1)), 2.0f);
+    const float* cy = p.gy + (int64_t)(gy - p.in_gy0) * p.ld_in + x;
+    if (gy == 0)
+        dy = __fsub_rn(__ldg(cy + p.ld_in), __ldg(cy));
+    else if (gy == p.gny - 1)
+        dy = __fsub_rn(__ldg(cy), __ldg(cy - p.ld_in));
+    else
+        dy = __fdiv_rn(__fsub_rn(__ldg(cy + p.ld_in), __ldg(cy - p.ld_in)), 2.0f);
+    finish_gradient(p, dx, dy, gy, x);
+}
+
+__global__ void __launch_bounds__(256) sobel_gradient_kernel(const GradParams p) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int gy = p.out_gy0 + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= p.nx || gy >= p.out_gy0 + p.out_rows) return;
+    const int xm = reflect_index(x - 1, p.nx), xp = reflect_index(x + 1, p.nx);
+    const float* r0 = p.gx + (int64_t)(reflect_index(gy - 1, p.gny) - p.in_gy0) * p.ld_in;
+    const float* r1 = p.gx + (int64_t)(gy - p.in_gy0) * p.ld_in;
+    const float* r2 = p.gx + (int64_t)(reflect_index(gy + 1, p.gny) - p.in_gy0) * p.ld_in;
+    const double a = __ldg(r0 + xm), b = __ldg(r0 + x), c = __ldg(r0 + xp);
+    const double d = __ldg(r1 + xm), f = __ldg(r1 + xp);
+    const double g = __ldg(r2 + xm), h = __ldg(r2 + x), i = __ldg(r2 + xp);
+    // exact in float64 (<= 6 terms of 24-bit values), one rounding to float32 like ndimage
+    const float dx = (float)(((c + 2.0 * f + i) - (a + 2.0 * d + g)) * 0.125);
+    const float dy = (float)(((g + 2.0 * h + i) - (a + 2.0 * b + c)) * 0.125);
+    finish_gradient(p, dx, dy, gy, x);
+}
+
+static int check_rows_reflect(const topo_view* v, int lo_off, int hi_off, const char* what) {
+    // rows out_gy0+lo_off .. out_gy0+out_rows-1+hi_off, reflected into the image, must be in the band
+    const int a = v->out_gy0 + lo_off, b = v->out_gy0 + v->out_rows - 1 + hi_off;
+    int need_lo = a < 0 ? 0 : a, need_hi = b >= v->gny ? v->gny - 1 : b;
+    if (-a > v->gny || b - v->gny + 1 > v->gny) need_lo = 0, need_hi = v->gny - 1;  // multiple reflections
+    if (a < 0) {  // reflection of [a, -1] is [0, -a-1]
+        int r = -a - 1;
+        if (r >= v->gny) r = v->gny - 1;
+        if (r > need_hi) need_hi = r;
+    }
+    if (b >= v->gny) {  // reflection of [gny, b] is [2*gny-1-b, gny-1]
+        int r = 2 * v->gny - 1 - b;
+        if (r < 0) r = 0;
+        if (r < need_lo) need_lo = r;
+    }
+    TOPO_CHECK(v->in_gy0 <= need_lo && v->in_gy0 + v->in_rows > need_hi,
+               "%s: input band [%d,%d) does not cover rows [%d,%d]", what, v->in_gy0, v->in_gy0 + v->in_rows,
+               need_lo, need_hi);
+    return 0;
+}
+
+}  // namespace topo
+
+using namespace topo;
+
+extern "C" {
+
+size_t topo_gauss_workspace_bytes(const topo_view* v, int lw_y, int lw_x) {
+    if (!v) return 0;
+    (void)lw_y, (void)lw_x;
+    // axis-0 result for the output rows (pitch = nx rounded to 4)
+    const size_t pitch = ((size_t)v->nx + 3) & ~(size_t)3;
+    return pitch * (size_t)(v->out_rows > 0 ? v->out_rows : 1) * sizeof(float);
+}
+
+int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
+                   const double* w_y, int lw_y, const double* w_x, int lw_x, void* ws, size_t ws_bytes,
+                   void* stream) {
+    TOPO_CHECK(in && out, "null pointer");
+    if (validate_view(v)) return -1;
+    TOPO_CHECK(ld_in >= v->nx && ld_out >= v->nx, "row pitch smaller than nx");
+    TOPO_CHECK(lw_y >= 0 && lw_x >= 0, "negative radius");
+    if (v->out_rows == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool do_y = w_y != nullptr, do_x = w_x != nullptr;
+    TOPO_CHECK(in != out, "in-place smoothing is not supported");
+
+    const float* cur = in;
+    int64_t cur_ld = ld_in;
+    int cur_gy0 = v->in_gy0, cur_rows = v->in_rows;
+    if (do_y) {
+        if (check_rows_reflect(v, -lw_y, lw_y, "gaussian axis 0")) return -1;
+        float* dst = out;
+        int64_t dst_ld = ld_out;
+        if (do_x) {
+            const int64_t pitch = ((int64_t)v->nx + 3) & ~(int64_t)3;
+            TOPO_CHECK(ws && ws_bytes >= (size_t)pitch * v->out_rows * sizeof(float), "workspace too small");
+            dst = (float*)ws;
+            dst_ld = pitch;
+        }
+        GaussParams p{cur, dst, cur_ld, dst_ld, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_y, lw_y};
+        dim3 grid(ceil_div(v->nx, 32), ceil_div(v->out_rows, 8 * kK));
+        const size_t smem = (size_t)(lw_y + 2) * sizeof(double);
+        TOPO_CHECK(smem <= 48 * 1024, "gaussian radius %d too large", lw_y);
+        TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<<<grid, dim3(32, 8), smem, s>>>(p));
+        cur = dst, cur_ld = dst_ld, cur_gy0 = v->out_gy0, cur_rows = v->out_rows;
+    } else {
+        TOPO_CHECK(v->in_gy0 <= v->out_gy0 && v->in_gy0 + v->in_rows >= v->out_gy0 + v->out_rows,
+                   "input band does not cover the output rows");
+    }
+    if (do_x) {
+        const int wcount = (lw_x + 2 + 1) & ~1;
+        int TR = 0, pitch = 0;
+        size_t smem = 0;
+        for (int tr : {32, 16, 8}) {
+            int pt = kA1Cols + 2 * lw_x;
+            pt |= 1;  // odd pitch: lanes (rows) hit distinct banks
+            const size_t b = (size_t)wcount * sizeof(double) + ((size_t)tr * pt + (size_t)tr * (kA1Cols + 1)) * sizeof(float);
+            if (b <= 220 * 1024) {
+                TR = tr, pitch = pt, smem = b;
+                break;
+            }
+        }
+        TOPO_CHECK(TR > 0, "gaussian radius %d too large for the shared-memory row tile", lw_x);
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        TOPO_CUDA(cudaGetDevice(&dev));
+        if (dev < 64 && !attr_set[dev]) {
+            TOPO_CUDA(cudaFuncSetAttribute(gauss_axis1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set[dev] = true;
+        }
+        GaussParams p{cur, out, cur_ld, ld_out, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_x, lw_x};
+        dim3 grid(ceil_div(v->nx, kA1Cols), ceil_div(v->out_rows, TR));
+        TOPO_LAUNCH("gauss_axis1", s, gauss_axis1_kernel<<<grid, 256, smem, s>>>(p, TR, pitch));
+    } else if (!do_y) {
+        TOPO_CUDA(cudaMemcpy2DAsync(out, ld_out * sizeof(float),
+                                    in + (int64_t)(v->out_gy0 - v->in_gy0) * ld_in, ld_in * sizeof(float),
+                                    (size_t)v->nx * sizeof(float), v->out_rows, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+static int run_grad(bool sobel, const float* gx, const float* gy, int64_t ld_in, float* dx, float* dy, float* slope,
+                    float* aspect, int64_t ld_out, const topo_view* v, const double* res_x, int res_x_2d,
+                    const double* res_y, int res_y_2d, int normalize, void* stream) {
+    TOPO_CHECK(gx && gy && dx && dy, "null pointer");
+    if (validate_view(v)) return -1;
+    TOPO_CHECK(v->nx >= 2 && v->gny >= 2, "gradient needs at least 2 x 2 pixels");
+    TOPO_CHECK(!normalize || (res_x && res_y), "missing resolution arrays");
+    if (v->out_rows == 0) return 0;
+    if (check_rows_reflect(v, -1, 1, sobel ? "sobel" : "gradient")) return -1;
+    GradParams p{gx, gy, dx, dy, slope, aspect, ld_in, ld_out, v->nx, v->gny, v->in_gy0, v->in_rows,
+                 v->out_gy0, v->out_rows, res_x, res_y, res_x_2d, res_y_2d, normalize};
+    dim3 grid(ceil_div(v->nx, 64), ceil_div(v->out_rows, 4));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (sobel)
+        TOPO_LAUNCH("sobel_gradient", s, sobel_gradient_kernel<<<grid, 256, 0, s>>>(p));
+    else
+        TOPO_LAUNCH("grad_from_smooth", s, grad_from_smooth_kernel<<<grid, 256, 0, s>>>(p));
+    return 0;
+}
+
+int topo_grad_from_smooth_f32(const float* gx, const float* gy, int64_t ld_in, float* dx, float* dy, float* slope,
+                              float* aspect, int64_t ld_out, const topo_view* v, const double* res_x, int res_x_2d,
+                              const double* res_y, int res_y_2d, void* stream) {
+    return run_grad(false, gx, gy, ld_in, dx, dy, slope, aspect, ld_out, v, res_x, res_x_2d, res_y, res_y_2d, 1, stream);
+}
+
+int topo_sobel_gradient_f32(const float* dem, int64_t ld_in, float* dx, float* dy, float* slope, float* aspect,
+                            int64_t ld_out, const topo_view* v, const double* res_x, int res_x_2d,
+                            const double* res_y, int res_y_2d, int normalize, void* stream) {
+    return run_grad(true, dem, dem, ld_in, dx, dy, slope, aspect, ld_out, v, res_x, res_x_2d, res_y, res_y_2d,
+                    normalize, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,287 @@
+"""Device-side plumbing: a DEM (or a row band of one) resident in HBM, and thin wrappers that launch
+the kernels of libtopo_b200.so on torch-owned buffers.
+
+PyTorch is used only for device memory, streams and (in ``bands.py``) ``torch.distributed``; every
+computation below is a call through the C ABI (``include/topo_b200.h``).  No CPU fallback exists: a
+missing library or GPU raises.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import View
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("topo_descriptors_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _lib.load()
+    return torch
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def to_device(array, pin=False):
+    """Host ndarray -> contiguous float32 CUDA tensor (H2D on the current stream)."""
+    torch = require_cuda()
+    a = np.ascontiguousarray(array, dtype=np.float32)
+    t = torch.from_numpy(a)
+    if pin:
+        t = t.pin_memory()
+    return t.to("cuda", non_blocking=pin)
+
+
+class DeviceDEM:
+    """A float32 raster band in HBM.
+
+    ``tensor``: (rows, nx) CUDA tensor holding global rows [gy0, gy0 + rows) of an image that is
+    ``gny`` rows tall (``gy0 = 0, gny = rows`` for a whole DEM).  ``stats`` are the GLOBAL DEM
+    statistics (lazily computed for a whole DEM; must be supplied for a band so that every band uses
+    the same fixed-point scale and z-score).
+    """
+
+    def __init__(self, tensor, gny=None, gy0=0, stats=None):
+        torch = require_cuda()
+        if isinstance(tensor, np.ndarray):
+            tensor = to_device(tensor)
+        if tensor.dtype != torch.float32 or tensor.dim() != 2 or not tensor.is_cuda:
+            raise TypeError("DeviceDEM needs a 2-D float32 CUDA tensor")
+        if tensor.stride(1) != 1:
+            tensor = tensor.contiguous()
+        self.tensor = tensor
+        self.rows, self.nx = int(tensor.shape[0]), int(tensor.shape[1])
+        self.ld = int(tensor.stride(0))
+        self.gy0 = int(gy0)
+        self.gny = int(self.rows if gny is None else gny)
+        self._stats = stats
+
+    @property
+    def is_whole(self):
+        return self.gy0 == 0 and self.rows == self.gny
+
+    @property
+    def stats(self):
+        if self._stats is None:
+            if not self.is_whole:
+                raise RuntimeError("a row band needs the global DEM statistics (see bands.global_stats)")
+            self._stats = dem_stats(self.tensor)
+        return self._stats
+
+    def view(self, out_gy0=None, out_rows=None):
+        """topo_view computing global rows [out_gy0, out_gy0+out_rows) from this band."""
+        if out_gy0 is None:
+            out_gy0, out_rows = self.gy0, self.rows
+        return View(self.nx, self.gny, self.gy0, self.rows, int(out_gy0), int(out_rows))
+
+
+def dem_stats(tensor):
+    """min / max / non-finite / non-integer / sum / sumsq / n of a device raster (one D2H of 64 B)."""
+    torch = require_cuda()
+    rows, nx = int(tensor.shape[0]), int(tensor.shape[1])
+    L = _lib.load()
+    ws_bytes = L.topo_dem_stats_workspace_bytes(rows, nx)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=tensor.device)
+    out = torch.empty(8, dtype=torch.float64, device=tensor.device)
+    _lib.call("topo_dem_stats_f32", _ptr(tensor), rows, nx, int(tensor.stride(0)), _ptr(out), _ptr(ws), ws_bytes,
+              _stream())
+    s = out.cpu().numpy()
+    return {
+        "min": float(s[0]), "max": float(s[1]), "nonfinite": int(s[2]), "nonint": int(s[3]),
+        "sum": float(s[4]), "sumsq": float(s[5]), "n": int(s[6]),
+    }
+
+
+def merge_stats(parts):
+    """Combine per-band statistics into global ones (used by the row-band driver)."""
+    return {
+        "min": min(p["min"] for p in parts), "max": max(p["max"] for p in parts),
+        "nonfinite": sum(p["nonfinite"] for p in parts), "nonint": sum(p["nonint"] for p in parts),
+        "sum": float(np.sum([p["sum"] for p in parts])), "sumsq": float(np.sum([p["sumsq"] for p in parts])),
+        "n": sum(p["n"] for p in parts),
+    }
+
+
+def _new(rows, nx, like):
+    return _torch().empty((rows, nx), dtype=_torch().float32, device=like.device)
+
+
+def fill(t, value):
+    _lib.call("topo_fill_f32", _ptr(t), int(t.shape[0]), int(t.shape[1]), int(t.stride(0)), float(value), _stream())
+
+
+def stamp(t, rows_dev, cols_dev, value=float("nan")):
+    """t[rows, cols] = value on device (``array[ind_nans] = np.nan`` of the compute_* drivers)."""
+    n = int(rows_dev.numel())
+    if n:
+        _lib.call("topo_stamp_f32", _ptr(t), int(t.stride(0)), _ptr(rows_dev), _ptr(cols_dev), n, float(value),
+                  _stream())
+
+
+# ---- Gaussian weights, exactly scipy's _gaussian_kernel1d (scipy/ndimage/_filters.py) -------------
+_WEIGHT_CACHE = {}
+
+
+def gaussian_half_kernel(sigma, truncate=4.0):
+    """(w, lw): w[0] centre .. w[lw]; float64, normalised by the float64 sum of the full kernel."""
+    sigma = float(sigma)
+    lw = int(truncate * sigma + 0.5)
+    x = np.arange(-lw, lw + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x**2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[lw:]), lw
+
+
+def _device_weights(sigma, device):
+    if sigma is None or float(sigma) <= 1e-15:
+        return None, 0
+    key = (float(sigma), str(device))
+    hit = _WEIGHT_CACHE.get(key)
+    if hit is None:
+        w, lw = gaussian_half_kernel(sigma)
+        hit = (_torch().from_numpy(w).to(device), lw)
+        if len(_WEIGHT_CACHE) > 256:
+            _WEIGHT_CACHE.clear()
+        _WEIGHT_CACHE[key] = hit
+    return hit
+
+
+def gauss_radius(sigma):
+    return 0 if sigma is None or float(sigma) <= 1e-15 else int(4.0 * float(sigma) + 0.5)
+
+
+def gauss(dem, sigma_y, sigma_x, out_gy0=None, out_rows=None, out=None):
+    """ndimage.gaussian_filter(dem, (sigma_y, sigma_x)) for global rows [out_gy0, out_gy0+out_rows)."""
+    torch = require_cuda()
+    v = dem.view(out_gy0, out_rows)
+    wy, lwy = _device_weights(sigma_y, dem.tensor.device)
+    wx, lwx = _device_weights(sigma_x, dem.tensor.device)
+    if out is None:
+        out = _new(v.out_rows, dem.nx, dem.tensor)
+    L = _lib.load()
+    ws_bytes = L.topo_gauss_workspace_bytes(ctypes.byref(v), lwy, lwx) if (wy is not None and wx is not None) else 0
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
+    _lib.call("topo_gauss_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), _ptr(wy), lwy,
+              _ptr(wx), lwx, _ptr(ws), ws_bytes, _stream())
+    return out
+
+
+def _nan_result(v, like, n=1):
+    outs = [_new(v.out_rows, v.nx, like) for _ in range(n)]
+    for o in outs:
+        fill(o, float("nan"))
+    return outs
+
+
+def tpi(dem, size, out_gy0=None, out_rows=None, out=None):
+    """Device TPI of global rows [out_gy0, out_gy0+out_rows); all-NaN if the DEM has non-finite values
+    (the reference's FFT convolution spreads them over the whole output)."""
+    torch = require_cuda()
+    v = dem.view(out_gy0, out_rows)
+    st = dem.stats
+    if out is None:
+        out = _new(v.out_rows, dem.nx, dem.tensor)
+    if st["nonfinite"] > 0:
+        fill(out, float("nan"))
+        return out
+    L = _lib.load()
+    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), 0)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
+    _lib.call("topo_tpi_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
+              st["min"], st["max"], _ptr(ws), ws_bytes, _stream())
+    return out
+
+
+def std(dem, size, out_gy0=None, out_rows=None, out=None):
+    """Device STD (float32; the host shim up-casts to float64 like the reference)."""
+    torch = require_cuda()
+    v = dem.view(out_gy0, out_rows)
+    st = dem.stats
+    if out is None:
+        out = _new(v.out_rows, dem.nx, dem.tensor)
+    if st["nonfinite"] > 0:
+        fill(out, float("nan"))
+        return out
+    L = _lib.load()
+    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), 1)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
+    _lib.call("topo_std_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
+              1 if st["nonint"] == 0 else 0, st["min"], st["max"], _ptr(ws), ws_bytes, _stream())
+    return out
+
+
+def _res_to_device(res, device):
+    r = np.ascontiguousarray(np.asarray(res, dtype=np.float64))
+    return _torch().from_numpy(r).to(device), int(r.ndim == 2)
+
+
+def gradient_from_smooth(gx, gy, res_x_dev, res_x_2d, res_y_dev, res_y_2d, out_gy0=None, out_rows=None):
+    """[dx, dy, slope, aspect] from smoothed bands gx (d/dx) and gy (d/dy) (same band geometry)."""
+    require_cuda()
+    v = gx.view(out_gy0, out_rows)
+    outs = [_new(v.out_rows, gx.nx, gx.tensor) for _ in range(4)]
+    _lib.call("topo_grad_from_smooth_f32", _ptr(gx.tensor), _ptr(gy.tensor), gx.ld, _ptr(outs[0]), _ptr(outs[1]),
+              _ptr(outs[2]), _ptr(outs[3]), int(outs[0].stride(0)), ctypes.byref(v), _ptr(res_x_dev), res_x_2d,
+              _ptr(res_y_dev), res_y_2d, _stream())
+    return outs
+
+
+def sobel_gradient(dem, res_x_dev=None, res_x_2d=0, res_y_dev=None, res_y_2d=0, normalize=True, out_gy0=None,
+                   out_rows=None):
+    """Sobel derivatives; with ``normalize`` also the resolution division + slope + aspect."""
+    require_cuda()
+    v = dem.view(out_gy0, out_rows)
+    n_out = 4 if normalize else 2
+    outs = [_new(v.out_rows, dem.nx, dem.tensor) for _ in range(n_out)]
+    _lib.call("topo_sobel_gradient_f32", _ptr(dem.tensor), dem.ld, _ptr(outs[0]), _ptr(outs[1]),
+              _ptr(outs[2]) if normalize else ctypes.c_void_p(0), _ptr(outs[3]) if normalize else ctypes.c_void_p(0),
+              int(outs[0].stride(0)), ctypes.byref(v), _ptr(res_x_dev), res_x_2d, _ptr(res_y_dev), res_y_2d,
+              1 if normalize else 0, _stream())
+    return outs
+
+
+def sx(dem, offsets_dev, inv_dist_dev, az_begin_dev, n_az, window, height, dy_min, dy_max, out_gy0=None,
+       out_rows=None):
+    """Sx for n_az azimuth sectors in one launch -> tensor (n_az, out_rows, nx)."""
+    torch = require_cuda()
+    v = dem.view(out_gy0, out_rows)
+    out = torch.empty((n_az, v.out_rows, dem.nx), dtype=torch.float32, device=dem.tensor.device)
+    _lib.call("topo_sx_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(1)), int(out.stride(0)),
+              ctypes.byref(v), _ptr(offsets_dev), _ptr(inv_dist_dev), _ptr(az_begin_dev), int(n_az), int(window),
+              float(height), int(dy_min), int(dy_max), _stream())
+    return out
+
+
+def zscore(dem, mean, sd):
+    """(dem - mean) / std in float32 (topo.py:429) -> DeviceDEM with the same band geometry."""
+    require_cuda()
+    out = _new(dem.rows, dem.nx, dem.tensor)
+    _lib.call("topo_zscore_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), dem.rows, dem.nx,
+              float(mean), float(sd), _stream())
+    return DeviceDEM(out, gny=dem.gny, gy0=dem.gy0, stats=dem._stats)
+
+
+def valley_ridge(dem_norm, bank, out_gy0=None, out_rows=None):
+    """Running (max, argmax) over the rotated-kernel bank -> (norm, dir) tensors."""
+    require_cuda()
+    v = dem_norm.view(out_gy0, out_rows)
+    norm = _new(v.out_rows, dem_norm.nx, dem_norm.tensor)
+    direction = _new(v.out_rows, dem_norm.nx, dem_norm.tensor)
+    _lib.call("topo_valley_ridge_f32", _ptr(dem_norm.tensor), dem_norm.ld, _ptr(norm), _ptr(direction),
+              int(norm.stride(0)), ctypes.byref(v), _ptr(bank["data"]), _ptr(bank["hw"]), _ptr(bank["off"]),
+              int(bank["n_angles"]), int(bank["n_ch"]), int(bank["hmax"]), int(bank["wmax"]), _stream())
+    return norm, direction

@@ -1,0 +1,465 @@
+"""Drop-in for ``topo_descriptors.topo`` (reference: topo_descriptors/topo.py) with every array
+kernel running on a B200 through libtopo_b200.so.
+
+Same function names, argument meaning, defaults, return types and exceptions as the reference
+(SURVEY.md section 8b).  Inputs are host arrays (numpy, an xarray DataArray, or the built-in
+``_xr.DataArray``); each call moves the DEM to HBM, launches the CUDA kernels and brings the result
+back, so callers see reference types.  To keep a DEM resident across calls pass a
+:class:`~topo_descriptors_b200.device.DeviceDEM` instead of an array: results then stay on the
+device as torch tensors (this is what the ``compute_*`` drivers do across scales).
+
+There is no CPU implementation in this package: without the built library or a CUDA device every
+function raises.
+"""
+
+import logging
+
+import numpy as np
+
+from . import CFG
+from . import _geometry as geo
+from . import _xr
+from . import device as dev
+from . import helpers as hlp
+from .device import DeviceDEM
+
+logger = logging.getLogger(__name__)
+
+
+# ---------------------------------------------------------------------------------------------
+# array <-> device marshalling
+# ---------------------------------------------------------------------------------------------
+class _Marshal:
+    """Remembers how the caller passed the DEM so the result can go back in the same form."""
+
+    def __init__(self, dem):
+        self.on_device = isinstance(dem, DeviceDEM)
+        self.container = None
+        if self.on_device:
+            self.ddem = dem
+            self.dtype = np.dtype(np.float32)
+            return
+        if _xr.is_dataarray(dem):
+            self.container = dem
+            values = dem.values
+        else:
+            values = np.asarray(dem)
+        if values.ndim != 2:
+            raise ValueError("dem must be a 2-D array")
+        self.dtype = values.dtype if values.dtype.kind == "f" else np.dtype(np.float64)
+        self.ddem = DeviceDEM(dev.to_device(values))
+
+    def back(self, tensor, dtype=None):
+        """Device tensor -> what the reference would have returned for this input type."""
+        if self.on_device:
+            return tensor
+        arr = tensor.cpu().numpy()
+        dtype = self.dtype if dtype is None else dtype
+        if arr.dtype != dtype:
+            arr = arr.astype(dtype)
+        if self.container is not None:
+            return self.container.copy(data=arr)
+        return arr
+
+
+def _smoothed(ddem, sigma):
+    """Optional Gaussian pre-smoothing (topo.py:172-173, 297-298, 426-427).  The smoothed surface is
+    a new DEM: its statistics (range, integrality) are recomputed."""
+    if not sigma:
+        return ddem
+    if not ddem.is_whole:
+        raise ValueError("pre-smoothing of a row band goes through bands.py (needs a wider halo)")
+    return DeviceDEM(dev.gauss(ddem, sigma, sigma))
+
+
+# ---------------------------------------------------------------------------------------------
+# smoothed DEM
+# ---------------------------------------------------------------------------------------------
+def compute_dem(dem_ds, scales, ind_nans=[], crop=None, outdir="."):
+    """Smoothed DEM for every scale, one file each (topo.py:16-59)."""
+    hlp.check_dem(dem_ds)
+    logger.info(f"***Starting dem computation for scales {scales} meters***")
+    if not hasattr(scales, "__iter__"):
+        scales = [scales]
+
+    scales_pxl, _ = hlp.scale_to_pixel(scales, dem_ds)
+    sigmas = scales_pxl / CFG.scale_std
+    ddem, nans = _resident(dem_ds, ind_nans)
+
+    for idx, sigma in enumerate(sigmas):
+        logger.info(f"Computing scale {scales[idx]} meters")
+        out = dev.gauss(ddem, sigma, sigma)
+        _finish_output(out, nans, dem_ds, _dem_name(scales[idx]), crop, outdir, "m")
+
+
+def dem(dem, sigma):
+    """Gaussian-smoothed DEM, ``scipy.ndimage.gaussian_filter(dem, sigma)`` semantics (topo.py:62-80)."""
+    m = _Marshal(dem)
+    sig = (sigma, sigma) if np.isscalar(sigma) else tuple(sigma)
+    return m.back(dev.gauss(m.ddem, sig[0], sig[1]))
+
+
+def _dem_name(scale):
+    return f"DEM_{scale}M"
+
+
+# ---------------------------------------------------------------------------------------------
+# TPI
+# ---------------------------------------------------------------------------------------------
+def compute_tpi(dem_ds, scales, smth_factors=None, ind_nans=[], crop=None, outdir="."):
+    """TPI for every scale, one file each (topo.py:88-141)."""
+    hlp.check_dem(dem_ds)
+    logger.info(f"***Starting TPI computation for scales {scales} meters***")
+    if not hasattr(scales, "__iter__"):
+        scales = [scales]
+    if not hasattr(smth_factors, "__iter__"):
+        smth_factors = [smth_factors] * len(scales)
+
+    scales_pxl, _ = hlp.scale_to_pixel(scales, dem_ds)
+    sigmas = hlp.get_sigmas(smth_factors, scales_pxl)
+    ddem, nans = _resident(dem_ds, ind_nans)
+
+    for idx, scale_pxl in enumerate(scales_pxl):
+        logger.info(f"Computing scale {scales[idx]} meters with smoothing factor {smth_factors[idx]} ...")
+        out = tpi(ddem, scale_pxl, sigma=sigmas[idx])
+        _finish_output(out, nans, dem_ds, _tpi_name(scales[idx], smth_factors[idx]), crop, outdir, "m")
+
+
+@hlp.timer
+def tpi(dem, size, sigma=None):
+    """Topographic position index: elevation minus the mean of the neighbours inside a disc of
+    diameter ``size`` pixels, centre excluded (topo.py:144-181).
+
+    Zero-padded borders normalised by the full neighbour count, like the reference's
+    ``signal.convolve(mode="same")``; any non-finite input value makes the whole output NaN (FFT
+    semantics).  Result dtype follows the input (float32 in -> float32 out).
+    """
+    m = _Marshal(dem)
+    return m.back(dev.tpi(_smoothed(m.ddem, sigma), int(size)))
+
+
+def _tpi_name(scale, smth_factor):
+    add = f"_SMTHFACT{smth_factor:.3g}" if smth_factor else ""
+    return f"TPI_{scale}M{add}"
+
+
+def circular_kernel(size):
+    """Disc mask of diameter ``size`` (a square for size < 5), float32 (topo.py:191-213).  Host-side
+    convenience only: the device derives the per-row half-widths itself."""
+    middle = int(size / 2)
+    if size < 5:
+        return np.ones((size, size), dtype=np.float32)
+    ii, jj = np.ogrid[:size, :size]
+    return ((ii - middle) ** 2 + (jj - middle) ** 2 <= middle**2).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# STD
+# ---------------------------------------------------------------------------------------------
+def compute_std(dem_ds, scales, smth_factors=None, ind_nans=[], crop=None, outdir="."):
+    """Local standard deviation for every scale, one file each (topo.py:216-269)."""
+    hlp.check_dem(dem_ds)
+    logger.info(f"***Starting STD computation for scales {scales} meters***")
+    if not hasattr(scales, "__iter__"):
+        scales = [scales]
+    if not hasattr(smth_factors, "__iter__"):
+        smth_factors = [smth_factors] * len(scales)
+
+    scales_pxl, _ = hlp.scale_to_pixel(scales, dem_ds)
+    sigmas = hlp.get_sigmas(smth_factors, scales_pxl)
+    ddem, nans = _resident(dem_ds, ind_nans)
+
+    for idx, scale_pxl in enumerate(scales_pxl):
+        logger.info(f"Computing scale {scales[idx]} meters with smoothing factor {smth_factors[idx]} ...")
+        out = std(ddem, scale_pxl, sigma=sigmas[idx])
+        _finish_output(out, nans, dem_ds, _std_name(scales[idx], smth_factors[idx]), crop, outdir, "m",
+                       dtype=np.float64)
+
+
+@hlp.timer
+def std(dem, size, sigma=None):
+    """Standard deviation inside a rolling disc of diameter ``size`` pixels (topo.py:272-307):
+    sqrt(clip((sum trunc(x)^2 - (sum x)^2/N) / (N-1), 0)), including the reference's
+    ``dem.astype("int32")`` truncation inside the squares.  Returns float64 like the reference (the
+    kernel computes the variance in exact integer / float64 arithmetic and stores float32).
+    """
+    m = _Marshal(dem)
+    return m.back(dev.std(_smoothed(m.ddem, sigma), int(size)), dtype=np.float64)
+
+
+def _std_name(scale, smth_factor):
+    add = f"_SMTHFACT{smth_factor:.3g}" if smth_factor else ""
+    return f"STD_{scale}M{add}"
+
+
+# ---------------------------------------------------------------------------------------------
+# valley / ridge
+# ---------------------------------------------------------------------------------------------
+def compute_valley_ridge(dem_ds, scales, mode, flat_list=[0, 0.15, 0.3], smth_factors=None, ind_nans=[], crop=None,
+                         outdir="."):
+    """Valley or ridge index (norm + direction) for every scale (topo.py:317-386)."""
+    hlp.check_dem(dem_ds)
+    logger.info(f"***Starting {mode} index computation for scales {scales} meters***")
+    if not hasattr(scales, "__iter__"):
+        scales = [scales]
+    if not hasattr(smth_factors, "__iter__"):
+        smth_factors = [smth_factors] * len(scales)
+
+    scales_pxl, _ = hlp.scale_to_pixel(scales, dem_ds)
+    sigmas = hlp.get_sigmas(smth_factors, scales_pxl)
+    ddem, nans = _resident(dem_ds, ind_nans)
+
+    for idx, scale_pxl in enumerate(scales_pxl):
+        logger.info(f"Computing scale {scales[idx]} meters with smoothing factor {smth_factors[idx]} ...")
+        names = _valley_ridge_names(scales[idx], mode, smth_factors[idx])
+        outs = valley_ridge(ddem, scale_pxl, mode, flat_list, sigmas[idx])
+        for out, name in zip(outs, names):
+            _finish_output(out, nans, dem_ds, name, crop, outdir, "1")
+
+
+_BANK_CACHE = {}
+
+
+def _device_bank(size, mode, flat_list, device):
+    key = (int(size), mode, tuple(float(f) for f in flat_list), str(device))
+    bank = _BANK_CACHE.get(key)
+    if bank is None:
+        import torch
+
+        host = geo.build_valley_bank(int(size), mode, flat_list)
+        bank = dict(host)
+        bank["data"] = torch.from_numpy(host["data"]).to(device)
+        bank["hw"] = torch.from_numpy(host["hw"]).to(device)
+        bank["off"] = torch.from_numpy(host["off"]).to(device)
+        if len(_BANK_CACHE) > 16:
+            _BANK_CACHE.clear()
+        _BANK_CACHE[key] = bank
+    return bank
+
+
+@hlp.timer
+def valley_ridge(dem, size, mode, flat_list=[0, 0.15, 0.3], sigma=None):
+    """Valley or ridge index (topo.py:389-453): the z-scored DEM is matched against V / U shaped
+    kernels of width ``size`` rotated through 0..179 degrees; returns ``[norm, direction]`` (float32)
+    where direction is the best angle (0 = W-E, 90 = S-N, clockwise).
+
+    The whole 180-angle bank runs in one kernel launch.  Reproduces the reference's 3-D convolution
+    (neighbouring flat-list kernels are summed per channel) and strict '>' argmax.
+    """
+    if mode not in ("valley", "ridge"):
+        raise ValueError(f"Unknown mode {mode!r}")
+    m = _Marshal(dem)
+    ddem = _smoothed(m.ddem, sigma)
+    st = ddem.stats
+    if st["nonfinite"] > 0:
+        # the FFT spreads NaN everywhere: no comparison ever succeeds, norm = clip(-inf) = 0
+        # (direction is uninitialised memory in the reference; 0 here)
+        zero = dev._new(ddem.rows, ddem.nx, ddem.tensor)
+        dev.fill(zero, 0.0)
+        return [m.back(zero, np.float32), m.back(zero.clone(), np.float32)]
+    mean64 = st["sum"] / st["n"]
+    var64 = max(st["sumsq"] / st["n"] - mean64 * mean64, 0.0)
+    normed = dev.zscore(ddem, np.float32(mean64), np.float32(np.sqrt(var64)))
+    bank = _device_bank(size, mode, flat_list, ddem.tensor.device)
+    norm, direction = dev.valley_ridge(normed, bank)
+    return [m.back(norm, np.float32), m.back(direction, np.float32)]
+
+
+def _valley_ridge_names(scale, mode, smth_factor):
+    add = f"_SMTHFACT{smth_factor:.3g}" if smth_factor else ""
+    return [f"{mode}_NORM_{scale}M{add}", f"{mode}_DIR_{scale}M{add}"]
+
+
+def _valley_kernels(size, flat_list):
+    """Z-scored V / U kernels (topo.py:466-499)."""
+    return geo.valley_kernels(size, flat_list)
+
+
+def _ridge_kernels(size, flat_list):
+    """Flipped-sign valley kernels (topo.py:502-518)."""
+    return geo.valley_kernels(size, flat_list) * -1
+
+
+def _rotate_kernels(kernel, angle):
+    """Rotated, re-normalised kernel stack (topo.py:521-531)."""
+    return geo.rotate_kernels(kernel, angle)
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient / slope / aspect
+# ---------------------------------------------------------------------------------------------
+def compute_gradient(dem_ds, scales, sig_ratios=1, ind_nans=[], crop=None, outdir="."):
+    """W-E / S-N derivatives, slope and aspect for every scale (topo.py:534-594)."""
+    hlp.check_dem(dem_ds)
+    logger.info(f"***Starting gradients computation for scales {scales} meters***")
+    if not hasattr(scales, "__iter__"):
+        scales = [scales]
+    if not hasattr(sig_ratios, "__iter__"):
+        sig_ratios = [sig_ratios] * len(scales)
+
+    scales_pxl, res_meters = hlp.scale_to_pixel(scales, dem_ds)
+    sigmas = scales_pxl / CFG.scale_std
+    ddem, nans = _resident(dem_ds, ind_nans)
+    all_units = ["1", "1", "degree", "degree"]
+
+    for idx, sigma in enumerate(sigmas):
+        logger.info(f"Computing scale {scales[idx]} meters with sigma ratio {sig_ratios[idx]} ...")
+        names = _gradient_names(scales[idx], sig_ratios[idx])
+        outs = gradient(ddem, sigma, res_meters, sig_ratio=sig_ratios[idx])
+        for out, name, units in zip(outs, names, all_units):
+            _finish_output(out, nans, dem_ds, name, crop, outdir, units)
+
+
+@hlp.timer
+def gradient(dem, sigma, res_meters, sig_ratio=1):
+    """Directional derivatives, slope and aspect (topo.py:597-644): ``[dx, dy, slope, aspect]``.
+
+    sigma <= 1: Sobel.  Otherwise central differences of the Gaussian-smoothed DEM (anisotropic
+    smoothing when ``sig_ratio != 1``), divided by the signed grid resolution ``res_meters`` (the
+    second return value of ``helpers.scale_to_pixel``); slope in degrees, aspect clockwise from
+    north.  float32, evaluated in the reference's own operation order.
+    """
+    m = _Marshal(dem)
+    d = m.ddem
+    device = d.tensor.device
+    rx, rx2d = dev._res_to_device(res_meters["x"], device)
+    ry, ry2d = dev._res_to_device(res_meters["y"], device)
+    if sigma <= 1:
+        outs = dev.sobel_gradient(d, rx, rx2d, ry, ry2d, normalize=True)
+    else:
+        if not d.is_whole:
+            raise ValueError("gradient of a row band goes through bands.py (needs a halo)")
+        if sig_ratio == 1:
+            gx = gy = DeviceDEM(dev.gauss(d, sigma, sigma))
+        else:
+            sigma_perp = sigma * sig_ratio
+            gx = DeviceDEM(dev.gauss(d, sigma_perp, sigma))
+            gy = DeviceDEM(dev.gauss(d, sigma, sigma_perp))
+        outs = dev.gradient_from_smooth(gx, gy, rx, rx2d, ry, ry2d)
+    return [m.back(o, np.float32) for o in outs]
+
+
+def _gradient_names(scale, sig_ratio):
+    tag = f"{scale}M_SIGRATIO{sig_ratio:.3g}"
+    return [f"WE_DERIVATIVE_{tag}", f"SN_DERIVATIVE_{tag}", f"SLOPE_{tag}", f"ASPECT_{tag}"]
+
+
+def sobel(dem):
+    """Sobel derivatives ``(dx, dy)`` in metres per pixel, reflect borders (topo.py:658-685)."""
+    m = _Marshal(dem)
+    dx, dy = dev.sobel_gradient(m.ddem, normalize=False)
+    return m.back(dx, np.float32), m.back(dy, np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Sx
+# ---------------------------------------------------------------------------------------------
+def compute_sx(dem_ds, azimuth, radius, height=10.0, azimuth_arc=10.0, azimuth_steps=15, radius_min=0.0, crop=None,
+               outdir="."):
+    """Sx for one azimuth, saved to file (topo.py:715-772)."""
+    hlp.check_dem(dem_ds)
+    logger.info(f"***Starting Sx computation for azimuth {azimuth} meters and radius {radius}***")
+    array = sx(dem_ds, azimuth, radius, height=height, azimuth_arc=azimuth_arc, azimuth_steps=azimuth_steps,
+               radius_min=radius_min)
+    hlp.to_netcdf(array, dem_ds, _sx_name(radius, azimuth), crop, outdir, "degree")
+
+
+def _sx_plan(dem_ds, azimuths_centre, radius, azimuth_arc, azimuth_steps, radius_min):
+    """Host geometry of topo.py:828-853 for one or several sector centres -> CSR sample lists."""
+    if azimuth_arc == 0:
+        azimuth_steps = 1
+    _, res_meters = hlp.scale_to_pixel(radius, dem_ds)
+    dx = res_meters["x"].mean()
+    dy = res_meters["y"].mean()
+    window_distance = geo.sx_distance(radius, dx, dy)
+    window_distance[window_distance < radius_min] = np.nan
+    centre = np.floor(np.array(window_distance.shape) / 2)
+    offs, invs, begin = [], [], [0]
+    window = int(window_distance.shape[0] / 2)
+    for az in azimuths_centre:
+        azimuths = np.linspace(az - azimuth_arc / 2, az + azimuth_arc / 2, azimuth_steps)
+        source = (centre + geo.sx_source_idx_delta(azimuths, radius, dx, dy)).astype(int)
+        lines = geo.sx_bresenhamlines(source, centre)
+        o, inv, window = geo.sx_samples(window_distance, lines)
+        offs.append(o)
+        invs.append(inv)
+        begin.append(begin[-1] + len(inv))
+    offsets = np.concatenate(offs) if offs else np.zeros((0, 2), np.int32)
+    inv = np.concatenate(invs) if invs else np.zeros(0, np.float32)
+    return offsets.reshape(-1, 2), inv, np.array(begin, dtype=np.int32), window
+
+
+def _sx_device(ddem, plan, height):
+    import torch
+
+    offsets, inv, begin, window = plan
+    device = ddem.tensor.device
+    off_d = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int32)).to(device)
+    inv_d = torch.from_numpy(np.ascontiguousarray(inv, dtype=np.float32)).to(device)
+    beg_d = torch.from_numpy(begin).to(device)
+    dy_min = int(offsets[:, 0].min()) if len(offsets) else 0
+    dy_max = int(offsets[:, 0].max()) if len(offsets) else 0
+    return dev.sx(ddem, off_d, inv_d, beg_d, len(begin) - 1, window, height, dy_min, dy_max)
+
+
+@hlp.timer
+def sx(dem_ds, azimuth, radius, height=10.0, azimuth_arc=10.0, azimuth_steps=15, radius_min=0.0):
+    """Sx (Winstral): the maximum slope angle, in degrees, towards the terrain lying within
+    ``radius`` metres in the sector ``azimuth`` +- ``azimuth_arc``/2 (topo.py:775-858).
+
+    ``dem_ds`` must be a Dataset (``TypeError`` otherwise, like the reference).  A frame of
+    radius-in-pixels cells along every edge is 0; NaN terrain samples are ignored; a NaN centre
+    gives NaN.  Returns a float32 array.  ``azimuth`` may also be a sequence: all sectors then run
+    in one launch and the result has a leading azimuth axis.
+    """
+    if not _xr.is_dataset(dem_ds):
+        raise TypeError("Argument 'dem_ds' must be a xr.Dataset.")
+    many = hasattr(azimuth, "__iter__")
+    centres = list(azimuth) if many else [azimuth]
+    plan = _sx_plan(dem_ds, centres, radius, azimuth_arc, azimuth_steps, radius_min)
+    values = hlp.get_da(dem_ds).values
+    ddem = values if isinstance(values, DeviceDEM) else DeviceDEM(dev.to_device(values))
+    out = _sx_device(ddem, plan, height).cpu().numpy()
+    return out if many else out[0]
+
+
+def _sx_distance(radius, dx, dy):
+    return geo.sx_distance(radius, dx, dy)
+
+
+def _sx_source_idx_delta(azimuths, radius, dx, dy):
+    return geo.sx_source_idx_delta(azimuths, radius, dx, dy)
+
+
+def _sx_bresenhamlines(start, end):
+    return geo.sx_bresenhamlines(start, end)
+
+
+def _sx_name(radius, azimuth):
+    return f"SX_RADIUS{int(radius)}_AZIMUTH{int(azimuth)}"
+
+
+# ---------------------------------------------------------------------------------------------
+# shared by the compute_* drivers: DEM residency and the output stage
+# ---------------------------------------------------------------------------------------------
+def _resident(dem_ds, ind_nans):
+    """Upload the DEM once for all scales; upload the NaN re-stamp indices once (topo.py:129,139)."""
+    import torch
+
+    ddem = DeviceDEM(dev.to_device(hlp.get_da(dem_ds).values))
+    nans = None
+    if ind_nans is not None and len(ind_nans) == 2 and len(ind_nans[0]):
+        rows = torch.from_numpy(np.ascontiguousarray(ind_nans[0], dtype=np.int32)).to(ddem.tensor.device)
+        cols = torch.from_numpy(np.ascontiguousarray(ind_nans[1], dtype=np.int32)).to(ddem.tensor.device)
+        nans = (rows, cols)
+    return ddem, nans
+
+
+def _finish_output(tensor, nans, dem_ds, name, crop, outdir, units, dtype=np.float32):
+    """``array[ind_nans] = np.nan`` on device, one D2H, then the reference's writer."""
+    if nans is not None:
+        dev.stamp(tensor, nans[0], nans[1])
+    array = tensor.cpu().numpy()
+    if array.dtype != dtype:
+        array = array.astype(dtype)
+    hlp.to_netcdf(array, dem_ds, name, crop, outdir, units)
