@@ -47,8 +47,8 @@ const char* topo_last_error(void);
  * `gpu_launches` claim). */
 long long topo_launch_count(void);
 /* Per-kernel timing for bench.py: while enabled, every launch is bracketed by CUDA events on its
- * stream.  topo_profile_dump synchronises on them, writes "<kernel> <launches> <total_ms> <max_ms>"
- * lines into buf and clears the records. */
+ * stream.  topo_profile_dump synchronises on them, writes one "<kernel> <ms>" line per launch (in
+ * launch order) into buf and clears the records. */
 int topo_profile_enable(int on);
 int topo_profile_dump(char* buf, size_t cap);
 

@@ -105,12 +105,21 @@ def profile_enable(on=True):
     load().topo_profile_enable(1 if on else 0)
 
 
-def profile_dump():
-    """{kernel name: {"launches": n, "ms": total, "max_ms": longest}} since the last dump."""
-    buf = ctypes.create_string_buffer(1 << 16)
+def profile_dump(aggregate=True):
+    """Kernel timings since the last dump.  aggregate=True: {name: {"launches", "ms", "max_ms"}};
+    aggregate=False: [(name, ms)] in launch order."""
+    buf = ctypes.create_string_buffer(1 << 20)
     call("topo_profile_dump", buf, len(buf))
-    out = {}
+    records = []
     for line in buf.value.decode().splitlines():
-        name, n, ms, mx = line.rsplit(" ", 3)
-        out[name] = {"launches": int(n), "ms": float(ms), "max_ms": float(mx)}
+        name, ms = line.rsplit(" ", 1)
+        records.append((name, float(ms)))
+    if not aggregate:
+        return records
+    out = {}
+    for name, ms in records:
+        a = out.setdefault(name, {"launches": 0, "ms": 0.0, "max_ms": 0.0})
+        a["launches"] += 1
+        a["ms"] += ms
+        a["max_ms"] = max(a["max_ms"], ms)
     return out

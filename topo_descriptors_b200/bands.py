@@ -1,0 +1,169 @@
+"""Row-band sharding of one large DEM over the GPUs of a box.
+
+One process per GPU (``torch.distributed``, NCCL on GPUs, gloo in the CPU tests).  Rank r owns the
+contiguous rows ``[r0, r1)`` of the global raster; before a descriptor runs, each rank receives the
+``halo`` rows above and below from its neighbours (NVLink send/recv through
+``torch.distributed.batch_isend_irecv``) and then calls the same kernels as the single-GPU path with a
+``topo_view`` that carries the global geometry, so borders (zero padding, reflect, one-sided
+differences, the Sx frame) are evaluated in global coordinates and every pixel is bit-identical to the
+single-GPU result.  The only collective besides the neighbour exchange is the tiny all-reduce that
+makes the DEM statistics (range -> fixed-point scale, mean/std -> z-score) global.
+
+The reference's own precedent is ``dask.array.map_overlap(depth=2*size)`` in ``tpi`` (topo.py:177-178).
+"""
+
+import numpy as np
+
+
+def partition_rows(gny, world):
+    """Balanced contiguous row ranges: [(r0, r1)] * world (first ``gny % world`` ranks get one more)."""
+    base, extra = divmod(int(gny), int(world))
+    out, r = [], 0
+    for k in range(world):
+        n = base + (1 if k < extra else 0)
+        out.append((r, r + n))
+        r += n
+    return out
+
+
+class BandContext:
+    """Where this rank sits in the row-band decomposition."""
+
+    def __init__(self, gny, nx, rank=0, world=1):
+        self.gny, self.nx, self.rank, self.world = int(gny), int(nx), int(rank), int(world)
+        self.parts = partition_rows(gny, world)
+        self.r0, self.r1 = self.parts[rank]
+
+    @property
+    def rows(self):
+        return self.r1 - self.r0
+
+    def halo_extent(self, halo):
+        """Global rows [a, b) this rank needs for a stencil reaching ``halo`` rows up and down."""
+        return max(0, self.r0 - halo), min(self.gny, self.r1 + halo)
+
+
+def exchange_halo(core, ctx, halo):
+    """core: (rows, nx) tensor with this rank's own rows.  Returns (band, gy0): the rows
+    [max(0, r0-halo), min(gny, r1+halo)) assembled from the neighbours' edge rows.
+
+    ``halo`` may span several neighbouring bands (a 20 km scale over thin bands): every rank sends
+    to each rank whose extended range overlaps its rows.  Single rank: returns ``core`` itself.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if ctx.world == 1 or halo <= 0:
+        return core, ctx.r0
+    a, b = ctx.halo_extent(halo)
+    band = torch.empty((b - a, ctx.nx), dtype=core.dtype, device=core.device)
+    band[ctx.r0 - a : ctx.r1 - a] = core
+    ops = []
+    keep = []
+    for other in range(ctx.world):
+        if other == ctx.rank:
+            continue
+        o0, o1 = ctx.parts[other]
+        # rows of `other` that I need
+        lo, hi = max(a, o0), min(b, o1)
+        if lo < hi:
+            ops.append(dist.P2POp(dist.irecv, band[lo - a : hi - a], other))
+        # rows of mine that `other` needs
+        oa, ob = max(0, o0 - halo), min(ctx.gny, o1 + halo)
+        lo, hi = max(oa, ctx.r0), min(ob, ctx.r1)
+        if lo < hi:
+            chunk = core[lo - ctx.r0 : hi - ctx.r0]
+            keep.append(chunk)
+            ops.append(dist.P2POp(dist.isend, chunk, other))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return band, a
+
+
+def global_stats(local, ctx, device=None):
+    """All-reduce per-band DEM statistics (device.dem_stats dicts) into global ones."""
+    if ctx.world == 1:
+        return dict(local)
+    import torch
+    import torch.distributed as dist
+
+    dev = device if device is not None else "cpu"
+    mn = torch.tensor([local["min"]], dtype=torch.float64, device=dev)
+    mx = torch.tensor([local["max"]], dtype=torch.float64, device=dev)
+    sm = torch.tensor([local["nonfinite"], local["nonint"], local["sum"], local["sumsq"], local["n"]],
+                      dtype=torch.float64, device=dev)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    sm = sm.cpu().numpy()
+    return {"min": float(mn.item()), "max": float(mx.item()), "nonfinite": int(sm[0]), "nonint": int(sm[1]),
+            "sum": float(sm[2]), "sumsq": float(sm[3]), "n": int(sm[4])}
+
+
+# ---------------------------------------------------------------------------------------------
+# the multi-scale sweep on one band (what bench.py times; also the engine of sharded compute_*)
+# ---------------------------------------------------------------------------------------------
+def sweep_halo(sizes, sigmas):
+    """Rows of raw DEM a rank needs beyond its own for a TPI/STD sweep over ``sizes`` and a gradient
+    sweep over ``sigmas``: disc radius, resp. Gaussian radius + 1 for the central difference."""
+    from . import device as dev
+
+    h = 0
+    for s in sizes:
+        h = max(h, int(s) // 2)
+    for sg in sigmas:
+        h = max(h, (dev.gauss_radius(sg) + 1) if sg > 1 else 1)
+    return h
+
+
+def sweep(core, ctx, sizes, sigmas, res_x, res_y, what=("tpi", "std", "gradient"), sink=None, stats=None):
+    """Run the TPI / STD / gradient multi-scale sweep for this rank's rows.
+
+    core : (rows, nx) float32 CUDA tensor, the rank's own rows of the DEM
+    sink : callable(name, scale_index, tensor) receiving every output band (rows r0..r1); default drops
+    Returns the number of descriptor calls issued.
+    """
+    from . import device as dev
+    from .device import DeviceDEM
+
+    halo = sweep_halo(sizes if ("tpi" in what or "std" in what) else [], sigmas if "gradient" in what else [])
+    band, gy0 = exchange_halo(core, ctx, halo)
+    if stats is None:
+        stats = global_stats(dev.dem_stats(core), ctx, device=core.device)
+    ddem = DeviceDEM(band, gny=ctx.gny, gy0=gy0, stats=stats)
+    calls = 0
+    rx, rx2d = res_x
+    ry, ry2d = res_y
+    for i, size in enumerate(sizes):
+        if "tpi" in what:
+            out = dev.tpi(ddem, size, ctx.r0, ctx.rows)
+            calls += 1
+            if sink:
+                sink("tpi", i, out)
+        if "std" in what:
+            out = dev.std(ddem, size, ctx.r0, ctx.rows)
+            calls += 1
+            if sink:
+                sink("std", i, out)
+    if "gradient" in what:
+        for i, sigma in enumerate(sigmas):
+            if sigma <= 1:
+                outs = dev.sobel_gradient(ddem, rx, rx2d, ry, ry2d, True, ctx.r0, ctx.rows)
+            else:
+                g0, g1 = max(0, ctx.r0 - 1), min(ctx.gny, ctx.r1 + 1)
+                g = DeviceDEM(dev.gauss(ddem, sigma, sigma, g0, g1 - g0), gny=ctx.gny, gy0=g0, stats=stats)
+                outs = dev.gradient_from_smooth(g, g, rx, rx2d, ry, ry2d, ctx.r0, ctx.rows)
+            calls += 1
+            if sink:
+                for nm, o in zip(("dx", "dy", "slope", "aspect"), outs):
+                    sink(nm, i, o)
+    return calls
+
+
+def numpy_partition_check(gny, world):
+    """Small self-check used by the tests: the partition tiles [0, gny) without gaps."""
+    parts = partition_rows(gny, world)
+    assert parts[0][0] == 0 and parts[-1][1] == gny
+    assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+    return np.array(parts)

@@ -3,7 +3,6 @@
 #include <string.h>
 
 #include <atomic>
-#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -217,29 +216,22 @@ int topo_profile_enable(int on) {
     return 0;
 }
 
-// Writes one line per kernel name: "<name> <launches> <total_ms> <max_ms>\n"; clears the records.
+// Writes one line per recorded launch, in launch order: "<name> <ms>\n"; clears the records.
 int topo_profile_dump(char* buf, size_t cap) {
     TOPO_CHECK(buf && cap > 0, "null buffer");
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    struct Agg { long n = 0; double ms = 0, mx = 0; };
-    std::map<std::string, Agg> agg;
+    std::string out;
+    char line[256];
     for (auto& r : g_prof) {
         float ms = 0.f;
         if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
-            Agg& a = agg[r.name];
-            a.n += 1, a.ms += ms;
-            if (ms > a.mx) a.mx = ms;
+            snprintf(line, sizeof(line), "%s %.6f\n", r.name, ms);
+            out += line;
         }
         cudaEventDestroy(r.start);
         cudaEventDestroy(r.stop);
     }
     g_prof.clear();
-    std::string out;
-    char line[256];
-    for (auto& kv : agg) {
-        snprintf(line, sizeof(line), "%s %ld %.6f %.6f\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.mx);
-        out += line;
-    }
     TOPO_CHECK(out.size() + 1 <= cap, "profile buffer too small (%zu needed)", out.size() + 1);
     memcpy(buf, out.c_str(), out.size() + 1);
     return 0;

@@ -73,6 +73,8 @@ struct DiscParams {
     // epilogue constants
     double inv_scale, inv_fscale, n, inv_nm1;
     long long n_ll;
+    double inv_n_nm1;  // 1 / (N * (N - 1))
+    int exact64;       // N*B - a^2 fits in 64-bit integers
     int excl;  // TPI: offset (excl, excl) of the excluded "mid point" (0 odd size, -1 even size)
 };
 
@@ -204,14 +206,25 @@ __device__ __forceinline__ float finish(const DiscParams& p, const unsigned long
             const int ey = gy + p.excl, ex = x + p.excl;
             ze = (ey >= 0 && ex >= 0) ? (double)__ldg(p.dem + (int64_t)(ey - p.in_gy0) * p.ld_in + ex) : 0.0;
         }
-        return (float)(z - (sum_z - ze) * p.inv_nm1);
+        // z - conv/(N-1) as (z*(N-1) - conv)/(N-1): the numerator is exact, so a constant or planar
+        // neighbourhood gives exactly 0
+        return (float)(fma(z, n - 1.0, -(sum_z - ze)) * p.inv_nm1);
     } else {
-        const long long st = (long long)acc[0] + p.n_ll * (long long)p.tmin;  // sum trunc(x)
-        const long long cm = (long long)p.cmid;
-        const long long s2i = (long long)acc[1] + 2ll * cm * st - p.n_ll * cm * cm;  // sum trunc(x)^2
-        double s1 = (double)st;
-        if constexpr (MODE == STD_F) s1 += (double)acc[2] * p.inv_fscale - n;
-        const double var = ((double)s2i - s1 * s1 / n) * p.inv_nm1;
+        // N*(N-1)*var = N*sum(t^2) - (sum x)^2, evaluated around cmid so that the integer part
+        //   N*B - a^2,  a = sum(t - cmid), B = sum((t - cmid)^2)
+        // is exact in 64-bit integers (=> exactly 0 on flat terrain); the fractional parts enter as
+        //   - F*(2a + F + 2*N*cmid),  F = sum frac(x)
+        const long long a = (long long)acc[0] - p.n_ll * (long long)(p.cmid - p.tmin);
+        double num;
+        if (p.exact64)
+            num = (double)(p.n_ll * (long long)acc[1] - a * a);
+        else
+            num = n * (double)acc[1] - (double)a * (double)a;
+        if constexpr (MODE == STD_F) {
+            const double F = (double)acc[2] * p.inv_fscale - n;
+            num -= F * (2.0 * (double)a + F + 2.0 * n * (double)p.cmid);
+        }
+        const double var = num * p.inv_n_nm1;
         return (float)sqrt(fmax(var, 0.0));
     }
 }
@@ -490,6 +503,8 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
     if (plan_geometry(v, size, narr_of(mode), max_rb(mode), pl)) return -1;
     p.n = n;
     p.n_ll = (long long)n;
+    p.inv_n_nm1 = 1.0 / (n * (n - 1.0));
+    p.exact64 = (n * (floor(trange / 2.0) + 1.0)) < 3.0e9;
     p.inv_nm1 = 1.0 / (n - 1.0);
     return 0;
 }

@@ -17,6 +17,7 @@
 namespace topo {
 
 constexpr int kK = 8;  // outputs per thread along the filter axis
+constexpr int kAxis1SmemMaxRadius = 64;  // wider axis-1 filters go through a transpose
 
 struct GaussParams {
     const float* in;
@@ -41,7 +42,9 @@ __device__ __forceinline__ double weight_at(const double* wsm, int t, int lw) {
 }
 
 // ---- axis 0 (along y) -----------------------------------------------------------------------------
-// block (32, 8): 32 columns x 8 row groups of K rows.
+// block (32, 8): 32 columns x 8 row groups of K rows.  Interior row groups (the whole input window lies
+// inside the image and the band) walk a pointer down the column; only groups that touch the global top
+// or bottom edge pay for the reflect index arithmetic.
 __global__ void __launch_bounds__(256) gauss_axis0_kernel(const GaussParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* wsm = reinterpret_cast<double*>(smem_raw);
@@ -59,19 +62,38 @@ __global__ void __launch_bounds__(256) gauss_axis0_kernel(const GaussParams p) {
     for (int k = 0; k < kK; ++k) acc[k] = 0.0, wr[k] = 0.0;
 
     const int in_end = p.in_gy0 + p.in_rows;
-    for (int t0 = -lw; t0 <= kK - 1 + lw; t0 += kK) {
+    const int nsteps = ((kK + 2 * lw + kK - 1) / kK) * kK;  // steps actually walked (multiple of K)
+    const int first = gy0 - lw, last = first + nsteps - 1;
+    const int lo_ok = p.in_gy0 > 0 ? p.in_gy0 : 0, hi_ok = in_end < p.gny ? in_end : p.gny;
+    if (first >= lo_ok && last < hi_ok) {
+        const float* ptr = p.in + (int64_t)(first - p.in_gy0) * p.ld_in + xc;
+        for (int t0 = -lw; t0 <= kK - 1 + lw; t0 += kK) {
 #pragma unroll
-        for (int s = 0; s < kK; ++s) {
-            const int t = t0 + s;
+            for (int s = 0; s < kK; ++s) {
 #pragma unroll
-            for (int k = kK - 1; k > 0; --k) wr[k] = wr[k - 1];
-            wr[0] = weight_at(wsm, t, lw);
-            const int g = reflect_index(gy0 + t, p.gny);
-            float v = 0.f;
-            if (g >= p.in_gy0 && g < in_end) v = __ldg(p.in + (int64_t)(g - p.in_gy0) * p.ld_in + xc);
-            const double dv = (double)v;
+                for (int k = kK - 1; k > 0; --k) wr[k] = wr[k - 1];
+                wr[0] = weight_at(wsm, t0 + s, lw);
+                const double dv = (double)__ldg(ptr);
+                ptr += p.ld_in;
 #pragma unroll
-            for (int k = 0; k < kK; ++k) acc[k] = fma(wr[k], dv, acc[k]);
+                for (int k = 0; k < kK; ++k) acc[k] = fma(wr[k], dv, acc[k]);
+            }
+        }
+    } else {
+        for (int t0 = -lw; t0 <= kK - 1 + lw; t0 += kK) {
+#pragma unroll
+            for (int s = 0; s < kK; ++s) {
+                const int t = t0 + s;
+#pragma unroll
+                for (int k = kK - 1; k > 0; --k) wr[k] = wr[k - 1];
+                wr[0] = weight_at(wsm, t, lw);
+                const int g = reflect_index(gy0 + t, p.gny);
+                float v = 0.f;
+                if (g >= p.in_gy0 && g < in_end) v = __ldg(p.in + (int64_t)(g - p.in_gy0) * p.ld_in + xc);
+                const double dv = (double)v;
+#pragma unroll
+                for (int k = 0; k < kK; ++k) acc[k] = fma(wr[k], dv, acc[k]);
+            }
         }
     }
     if (x < p.nx) {
@@ -80,6 +102,23 @@ __global__ void __launch_bounds__(256) gauss_axis0_kernel(const GaussParams p) {
             const int gy = gy0 + k;
             if (gy < p.out_gy0 + p.out_rows) p.out[(int64_t)(gy - p.out_gy0) * p.ld_out + x] = (float)acc[k];
         }
+    }
+}
+
+// 32 x 32 tiled transpose (rows x cols -> cols x rows); lets the wide-radius axis-1 pass reuse the
+// column kernel above at full lane occupancy.
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t ld_in,
+                                                        float* __restrict__ out, int64_t ld_out, int rows, int cols) {
+    __shared__ float t[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) t[i][threadIdx.x] = __ldg(in + (int64_t)r * ld_in + c);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) out[(int64_t)c * ld_out + r] = t[threadIdx.x][i];
     }
 }
 
@@ -165,13 +204,22 @@ struct GradParams {
     int res_x_2d, res_y_2d, normalize;
 };
 
+// float32 value / float64 resolution, rounded to float32.  When the resolution is exactly representable in
+// float32 (25.0, 30.0, float32-derived UTM spacings ...) the IEEE float32 division gives the same correctly
+// rounded quotient without the float64 divide.
+__device__ __forceinline__ float div_by_res(float v, double r) {
+    const float rf = (float)r;
+    if ((double)rf == r) return __fdiv_rn(v, rf);
+    return (float)((double)v / r);
+}
+
 __device__ __forceinline__ void finish_gradient(const GradParams& p, float dx, float dy, int gy, int x) {
     if (p.normalize) {
         // `dx /= res` with a float64 resolution array: float64 division, rounded back to float32
         const double rx = p.res_x_2d ? p.res_x[(int64_t)gy * p.nx + x] : p.res_x[x];
         const double ry = p.res_y_2d ? p.res_y[(int64_t)gy * p.nx + x] : p.res_y[gy];
-        dx = (float)((double)dx / rx);
-        dy = (float)((double)dy / ry);
+        dx = div_by_res(dx, rx);
+        dy = div_by_res(dy, ry);
     }
     const int64_t o = (int64_t)(gy - p.out_gy0) * p.ld_out + x;
     p.dx[o] = dx;
@@ -261,10 +309,14 @@ extern "C" {
 
 size_t topo_gauss_workspace_bytes(const topo_view* v, int lw_y, int lw_x) {
     if (!v) return 0;
-    (void)lw_y, (void)lw_x;
-    // axis-0 result for the output rows (pitch = nx rounded to 4)
+    (void)lw_y;
+    const size_t rows = (size_t)(v->out_rows > 0 ? v->out_rows : 1);
+    // axis-0 result for the output rows (pitch = nx rounded to 4) ...
     const size_t pitch = ((size_t)v->nx + 3) & ~(size_t)3;
-    return pitch * (size_t)(v->out_rows > 0 ? v->out_rows : 1) * sizeof(float);
+    size_t bytes = pitch * rows * sizeof(float);
+    // ... plus two transposed planes when the axis-1 radius takes the transpose route
+    if (lw_x > kAxis1SmemMaxRadius) bytes += 2 * ((rows + 3) & ~(size_t)3) * (size_t)v->nx * sizeof(float);
+    return bytes;
 }
 
 int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
@@ -302,7 +354,26 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
         TOPO_CHECK(v->in_gy0 <= v->out_gy0 && v->in_gy0 + v->in_rows >= v->out_gy0 + v->out_rows,
                    "input band does not cover the output rows");
     }
-    if (do_x) {
+    if (do_x && lw_x > kAxis1SmemMaxRadius) {
+        // wide radius: transpose -> column kernel -> transpose back (two extra 8 B/px passes are noise next
+        // to 2*lw+1 float64 FMAs per pixel)
+        const int64_t pitch = ((int64_t)v->nx + 3) & ~(int64_t)3;
+        const int64_t tpitch = ((int64_t)v->out_rows + 3) & ~(int64_t)3;
+        const size_t need = (size_t)pitch * v->out_rows * sizeof(float) + 2 * (size_t)tpitch * v->nx * sizeof(float);
+        TOPO_CHECK(ws && ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        float* t1 = (float*)ws + (size_t)pitch * v->out_rows;
+        float* t2 = t1 + (size_t)tpitch * v->nx;
+        const float* src = cur + (int64_t)(v->out_gy0 - cur_gy0) * cur_ld;
+        dim3 tg(ceil_div(v->nx, 32), ceil_div(v->out_rows, 32));
+        TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(src, cur_ld, t1, tpitch, v->out_rows, v->nx));
+        GaussParams p{t1, t2, tpitch, tpitch, v->out_rows, v->nx, 0, v->nx, 0, v->nx, w_x, lw_x};
+        dim3 grid(ceil_div(v->out_rows, 32), ceil_div(v->nx, 8 * kK));
+        const size_t smem = (size_t)(lw_x + 2) * sizeof(double);
+        TOPO_CHECK(smem <= 48 * 1024, "gaussian radius %d too large", lw_x);
+        TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<<<grid, dim3(32, 8), smem, s>>>(p));
+        dim3 tg2(ceil_div(v->out_rows, 32), ceil_div(v->nx, 32));
+        TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg2, dim3(32, 8), 0, s>>>(t2, tpitch, out, ld_out, v->nx, v->out_rows));
+    } else if (do_x) {
         const int wcount = (lw_x + 2 + 1) & ~1;
         int TR = 0, pitch = 0;
         size_t smem = 0;

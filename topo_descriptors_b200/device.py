@@ -173,7 +173,7 @@ def gauss(dem, sigma_y, sigma_x, out_gy0=None, out_rows=None, out=None):
     if out is None:
         out = _new(v.out_rows, dem.nx, dem.tensor)
     L = _lib.load()
-    ws_bytes = L.topo_gauss_workspace_bytes(ctypes.byref(v), lwy, lwx) if (wy is not None and wx is not None) else 0
+    ws_bytes = L.topo_gauss_workspace_bytes(ctypes.byref(v), lwy, lwx)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
     _lib.call("topo_gauss_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), _ptr(wy), lwy,
               _ptr(wx), lwx, _ptr(ws), ws_bytes, _stream())
