@@ -78,12 +78,13 @@ int topo_stamp_f32(float* out, int64_t ld, const int* rows, const int* cols, int
  *        host up-casts to float64 like the reference).  trunc(x) reproduces
  *        `dem.astype("int32") ** 2` (topo.py:300): the squares use the truncated elevation.
  * zmin/zmax: GLOBAL finite range of the DEM (from topo_dem_stats_f32); all_integer: 1 if every
- * value is integral (enables the 2-array exact path for STD).
- * Small/medium sizes run fused (tile + halo prefix in shared memory); large sizes run two passes
- * through `ws`. */
+ * value is integral (SRTM-like DEMs: exact one-plane TPI, two-plane STD).
+ * Small sizes run fused (tile + halo prefix in shared memory); larger sizes run two passes through
+ * `ws` (prefix planes in HBM, gathered with 64-bit loads). */
 size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi, 1 std*/);
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
-                 int size, double zmin, double zmax, void* ws, size_t ws_bytes, void* stream);
+                 int size, int all_integer, double zmin, double zmax, void* ws, size_t ws_bytes,
+                 void* stream);
 int topo_std_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
                  int size, int all_integer, double zmin, double zmax, void* ws,
                  size_t ws_bytes, void* stream);

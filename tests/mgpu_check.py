@@ -1,0 +1,61 @@
+"""Multi-GPU band check (run under torchrun on a GPU box; not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+
+Every rank computes its row band of TPI / STD / gradient through bands.sweep (halo exchange over NCCL) and
+compares it BIT FOR BIT with the same rows of the whole-image result computed locally on its own GPU.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from topo_descriptors_b200 import bands, device as dev  # noqa: E402
+from topo_descriptors_b200.device import DeviceDEM  # noqa: E402
+from topo_descriptors_b200.synth import fractal_dem  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    ny, nx = 1500, 1111
+    bad = 0
+    for integer in (True, False):
+        z = fractal_dem(ny, nx, seed=5, integer=integer)
+        whole = DeviceDEM(torch.from_numpy(z).to(device))
+        ctx = bands.BandContext(ny, nx, rank, world)
+        core = whole.tensor[ctx.r0 : ctx.r1].contiguous()
+        sizes = [5, 21, 67, 201, 301]
+        sigmas = [1.25, 5.25, 16.75, 50.25, 75.25]
+        rx = (torch.full((nx,), 25.0, dtype=torch.float64, device=device), 0)
+        ry = (torch.full((ny,), -25.0, dtype=torch.float64, device=device), 0)
+        got = {}
+        bands.sweep(core, ctx, sizes, sigmas, rx, ry, sink=lambda n, i, t: got.__setitem__((n, i), t.clone()))
+        for i, size in enumerate(sizes):
+            ref = {"tpi": dev.tpi(whole, size), "std": dev.std(whole, size)}
+            g = DeviceDEM(dev.gauss(whole, sigmas[i], sigmas[i]))
+            outs = dev.gradient_from_smooth(g, g, rx[0], 0, ry[0], 0)
+            ref.update(dict(zip(("dx", "dy", "slope", "aspect"), outs)))
+            for name, r in ref.items():
+                same = torch.equal(got[(name, i)], r[ctx.r0 : ctx.r1])
+                if not same:
+                    bad += 1
+                    d = (got[(name, i)] - r[ctx.r0 : ctx.r1]).abs().max().item()
+                    print(f"rank {rank}: MISMATCH {name} size {size} integer={integer} max diff {d}", flush=True)
+    t = torch.tensor([bad], device=device)
+    dist.all_reduce(t)
+    if rank == 0:
+        print("mgpu_check:", "OK (bands bit-identical to the whole image)" if t.item() == 0 else f"{int(t.item())} mismatches")
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,25 +3,28 @@
 //
 // Method (north star: "per-row prefix-sum span-sum kernel"):
 //   every DEM value becomes one or more unsigned 32-bit integers (fixed point / exact integer parts),
-//   each tile row gets an exclusive prefix sum in WRAP-AROUND uint32 arithmetic, and a disc sum is
+//   each row gets an exclusive prefix sum in WRAP-AROUND uint32 arithmetic, and a disc sum is
 //   sum over kernel rows of  P[row][hi+1] - P[row][lo]  (exact modulo 2^32, and the true span sum
-//   is < 2^32 by construction of the scale), accumulated in 64-bit integers.  The epilogue is
-//   float64.  Integer arithmetic makes the result independent of tiling and of the row-band
-//   partition (bit-identical on 1 or 8 GPUs).
+//   is < 2^32 by construction of the scale).  The row differences are accumulated in 32-bit integers
+//   when the whole disc sum provably fits (one IADD3 per pixel and kernel row), else in 64-bit integers.
+//   The epilogue is float64 with an exact integer numerator.  Integer arithmetic makes the result
+//   independent of tiling and of the row-band partition (bit-identical on 1 or 8 GPUs).
 //
-// Modes (what the uint32 planes hold):
-//   TPI_Q : q = rn(z * 2^S) - c0*2^S                 1 plane, |error of the mean| <= 2^-(S+1)
-//   TPI_X : t - tmin,  (frac + 1) * 2^Sf             2 planes, exact (used when S would be < 10)
-//   STD_I : t - tmin,  (t - cmid)^2                  2 planes, exact (integer-valued DEM)
-//   STD_F : t - tmin,  (t - cmid)^2, (frac+1)*2^Sf   3 planes, exact
-//   with t = trunc(z) (the reference's astype("int32"), topo.py:300) and frac = z - t.
+// Modes (what the uint32 planes hold), t = trunc(z) (the reference's astype("int32"), topo.py:300),
+// frac = z - t:
+//   TPI_I : t - tmin                                  1 plane, exact (integer-valued DEM)
+//   TPI_Q : q = rn(z * 2^S) - c0*2^S                  1 plane, |error of the mean| <= 2^-(S+1)
+//   TPI_X : t - tmin,  (frac + 1) * 2^Sf              2 planes, exact (used when S would be < 10)
+//   STD_I : t - tmin,  (t - cmid)^2                   2 planes, exact (integer-valued DEM)
+//   STD_F : t - tmin,  (t - cmid)^2, (frac+1)*2^Sf    3 planes, exact
 //
-// Two execution shapes:
-//   fused    : CTA = 128-column x TH-row output tile; tile + halo is loaded with 128-bit loads,
-//              converted, scanned with warp shuffles into shared memory, then each thread walks the
-//              kernel rows for RB output rows of one column (conflict-free LDS, lanes = columns).
-//   two-pass : for discs whose halo does not fit shared memory the prefix planes go to global
-//              memory (workspace) and the span walk reads them through L1/L2.
+// Two execution shapes, same span walk (a thread owns 2 adjacent pixels x RB rows):
+//   fused    : CTA = 128 x 32 output tile; tile + halo is loaded with 128-bit loads, converted, scanned
+//              with warp shuffles into shared memory; lanes = pixel pairs => conflict-free LDS.
+//   two-pass : prefix planes go to HBM (workspace) in two copies, P and P shifted by one element, so that
+//              the pair (P[j], P[j+1]) is always one aligned 64-bit load; the span walk gathers them
+//              through L1/L2 with LDG.64 (measured 29.9 words/clk/SM vs 19.5 for LDG.32).  CTAs are
+//              rasterised in 16-tile-wide super-columns so that the rows in flight stay L2-resident.
 #include <math.h>
 #include <string.h>
 
@@ -31,12 +34,14 @@
 
 namespace topo {
 
-enum DiscMode { TPI_Q = 0, TPI_X = 1, STD_I = 2, STD_F = 3 };
+enum DiscMode { TPI_Q = 0, TPI_X = 1, STD_I = 2, STD_F = 3, TPI_I = 4 };
 
 template <int MODE>
 struct ModeTraits;
 template <>
 struct ModeTraits<TPI_Q> { static constexpr int NARR = 1; static constexpr int RB = 8; };
+template <>
+struct ModeTraits<TPI_I> { static constexpr int NARR = 1; static constexpr int RB = 8; };
 template <>
 struct ModeTraits<TPI_X> { static constexpr int NARR = 2; static constexpr int RB = 4; };
 template <>
@@ -44,26 +49,28 @@ struct ModeTraits<STD_I> { static constexpr int NARR = 2; static constexpr int R
 template <>
 struct ModeTraits<STD_F> { static constexpr int NARR = 3; static constexpr int RB = 4; };
 
-constexpr int kTW = 128;        // output tile width  (4 warps of columns)
-constexpr int kThreads = 256;   // 8 warps: 4 across x, 2 row groups
+constexpr int kTW = 128;        // output tile width: 64 threads x 2 pixels
+constexpr int kTH = 32;         // output tile height: 4 row groups x 8 rows
+constexpr int kThreads = 256;   // 8 warps
 constexpr int kMaxSize = 8191;  // span table lives in shared memory (4 B per kernel row)
+constexpr int kSuperCols = 16;  // two-pass raster: tiles per super-column
 
 struct DiscParams {
     const float* dem;
     float* out;
-    uint32_t* planes;  // two-pass: global prefix planes; fused: unused
+    uint32_t* planes;  // two-pass: global prefix planes (2 copies per plane); fused: unused
     int64_t ld_in, ld_out;
-    int64_t plane_stride;  // elements between planes
+    int64_t plane_stride;  // elements between consecutive plane copies
     int nx, gny, in_gy0, in_rows, out_gy0, out_rows;
     int k;       // kernel size
     int c;       // (k-1)/2 : scipy 'same' centring
     int mid;     // k/2     : circular_kernel's middle
     int square;  // size < 5
     int halo;    // k/2, rows/cols of halo on each side
-    int haloL;   // left halo rounded up to a multiple of 4 (keeps 128-bit loads aligned)
-    int TH;      // tile rows (fused) / rows per CTA (two-pass)
-    int pitch;   // prefix row pitch in elements
+    int haloL;   // left halo rounded up to a multiple of 8 (keeps 128-bit loads / 64-bit pairs aligned)
+    int pitch;   // prefix row pitch in elements (multiple of 8)
     int prow0;   // two-pass: global row of prefix row 0
+    int tiles_x, tiles_y;
     // conversion constants
     float scale;   // 2^S
     int c0i;       // c0 * 2^S            (TPI_Q)
@@ -75,7 +82,7 @@ struct DiscParams {
     long long n_ll;
     double inv_n_nm1;  // 1 / (N * (N - 1))
     int exact64;       // N*B - a^2 fits in 64-bit integers
-    int excl;  // TPI: offset (excl, excl) of the excluded "mid point" (0 odd size, -1 even size)
+    int excl;          // TPI: offset (excl, excl) of the excluded "mid point" (0 odd size, -1 even size)
 };
 
 // ---- span table: kernel row i -> (dxlo, dxhi) of its run of ones, as DEM column offsets ------------
@@ -141,47 +148,56 @@ __device__ __forceinline__ float4 load4_zero(const DiscParams& p, int gy, int x,
     return r;
 }
 
-// One warp scans one row: W elements starting at global column xs (multiple of 4) into the exclusive
-// prefix dst[a][0..W] of each plane a (dst rows have `pitch` elements, 16-byte aligned).
-template <int MODE>
+// One warp scans one row: W elements starting at global column xs (multiple of 8) into the exclusive
+// prefix dstA[a][0..W] of each plane a (rows have `pitch` >= W + 8 elements, 32-byte aligned).  With
+// COPIES == 2 the shifted copy dstB[a][k] = P[k+1] is written too.  8 elements per lane and chunk.
+template <int MODE, int COPIES>
 __device__ __forceinline__ void scan_row(const DiscParams& p, int gy, int xs, int W, uint32_t* dst,
                                          int64_t plane_stride, bool aligned, int lane) {
     constexpr int NARR = ModeTraits<MODE>::NARR;
     uint32_t carry[NARR];
 #pragma unroll
     for (int a = 0; a < NARR; ++a) carry[a] = 0u;
-    const int nchunks = (W + 127) >> 7;
+    const int nchunks = (W + 255) >> 8;
     for (int ch = 0; ch < nchunks; ++ch) {
-        const int lc = (ch << 7) + (lane << 2);
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lc < W) z = load4_zero(p, gy, xs + lc, aligned);
-        uint32_t v0[NARR], v1[NARR], v2[NARR], v3[NARR];
-        convert<MODE>(p, z.x, v0);
-        convert<MODE>(p, z.y, v1);
-        convert<MODE>(p, z.z, v2);
-        convert<MODE>(p, z.w, v3);
+        const int lc = (ch << 8) + (lane << 3);
+        float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0;
+        if (lc < W) z0 = load4_zero(p, gy, xs + lc, aligned);
+        if (lc + 4 < W) z1 = load4_zero(p, gy, xs + lc + 4, aligned);
+        const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        uint32_t v[8][NARR];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) convert<MODE>(p, zz[j], v[j]);
 #pragma unroll
         for (int a = 0; a < NARR; ++a) {
             // elements past W must not contribute (they convert to a non-zero "zero" otherwise)
-            uint32_t e0 = (lc + 0 < W) ? v0[a] : 0u;
-            uint32_t e1 = (lc + 1 < W) ? v1[a] : 0u;
-            uint32_t e2 = (lc + 2 < W) ? v2[a] : 0u;
-            uint32_t e3 = (lc + 3 < W) ? v3[a] : 0u;
-            const uint32_t s1 = e0 + e1, s2 = s1 + e2, tot = s2 + e3;
-            const uint32_t incl = warp_inclusive_scan_u32(tot, lane);
-            const uint32_t base = carry[a] + incl - tot;  // exclusive prefix at element lc
+            uint32_t s[8];
+            uint32_t run = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                run += (lc + j < W) ? v[j][a] : 0u;
+                s[j] = run;  // inclusive within the lane
+            }
+            const uint32_t incl = warp_inclusive_scan_u32(run, lane);
+            const uint32_t base = carry[a] + incl - run;  // exclusive prefix at element lc
             if (lc < W) {
-                uint4 o = make_uint4(base, base + e0, base + s1, base + s2);
-                *reinterpret_cast<uint4*>(dst + a * plane_stride + lc) = o;
+                uint32_t* d = dst + (int64_t)(COPIES * a) * plane_stride + lc;
+                *reinterpret_cast<uint4*>(d) = make_uint4(base, base + s[0], base + s[1], base + s[2]);
+                *reinterpret_cast<uint4*>(d + 4) = make_uint4(base + s[3], base + s[4], base + s[5], base + s[6]);
+                if constexpr (COPIES == 2) {
+                    uint32_t* e = d + plane_stride;
+                    *reinterpret_cast<uint4*>(e) = make_uint4(base + s[0], base + s[1], base + s[2], base + s[3]);
+                    *reinterpret_cast<uint4*>(e + 4) = make_uint4(base + s[4], base + s[5], base + s[6], base + s[7]);
+                }
             }
             carry[a] += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
-    // closing element P[W4] (W4 = W rounded up to 4): total of the row
+    // closing element P[W8] (W8 = W rounded up to 8): total of the row (P[W] itself when W % 8 == 0)
     if (lane == 0) {
-        const int W4 = (W + 3) & ~3;
+        const int W8 = (W + 7) & ~7;
 #pragma unroll
-        for (int a = 0; a < NARR; ++a) dst[a * plane_stride + W4] = carry[a];
+        for (int a = 0; a < NARR; ++a) dst[(int64_t)(COPIES * a) * plane_stride + W8] = carry[a];
     }
 }
 
@@ -190,14 +206,15 @@ template <int MODE>
 __device__ __forceinline__ float finish(const DiscParams& p, const unsigned long long (&acc)[ModeTraits<MODE>::NARR],
                                         int gy, int x) {
     const double n = p.n;
-    if constexpr (MODE == TPI_Q || MODE == TPI_X) {
+    if constexpr (MODE == TPI_Q || MODE == TPI_X || MODE == TPI_I) {
         double sum_z;
         if constexpr (MODE == TPI_Q) {
             const long long tot = (long long)acc[0] + p.n_ll * (long long)p.c0i;
             sum_z = (double)tot * p.inv_scale;
         } else {
             const long long st = (long long)acc[0] + p.n_ll * (long long)p.tmin;
-            sum_z = (double)st + ((double)acc[1] * p.inv_fscale - n);
+            sum_z = (double)st;
+            if constexpr (MODE == TPI_X) sum_z += (double)acc[1] * p.inv_fscale - n;
         }
         const float* row = p.dem + (int64_t)(gy - p.in_gy0) * p.ld_in;
         const double z = (double)__ldg(row + x);
@@ -229,97 +246,162 @@ __device__ __forceinline__ float finish(const DiscParams& p, const unsigned long
     }
 }
 
-// ---- the span walk: RB output rows of one column -----------------------------------------------------
-// P: prefix planes; row index `prow` of the prefix row that corresponds to the FIRST of the RB output
-// rows at kernel offset dy = 0; lcx: prefix column of the pixel itself.
-template <int MODE, bool GLOBAL>
+// ---- the span walk: RB output rows x 2 adjacent pixels ------------------------------------------------
+// prow: prefix row of the FIRST of the RB output rows at kernel offset dy = 0; lcx: prefix column of the
+// first pixel (two-pass: even, second pixel adjacent; fused: second pixel 64 columns to the right).  ACC: bit a set => plane a's whole disc sum fits 32 bits (one IADD3 per row).
+template <int MODE, int ACC, bool GLOBAL>
 __device__ __forceinline__ void span_walk(const DiscParams& p, const uint32_t* __restrict__ P, int64_t plane_stride,
                                           int pitch, const int* __restrict__ tab, int prow, int lcx,
-                                          unsigned long long (&acc)[ModeTraits<MODE>::RB][ModeTraits<MODE>::NARR]) {
+                                          unsigned long long (&out)[ModeTraits<MODE>::RB][2][ModeTraits<MODE>::NARR]) {
     constexpr int NARR = ModeTraits<MODE>::NARR;
     constexpr int RB = ModeTraits<MODE>::RB;
-    using idx_t = typename std::conditional<GLOBAL, int64_t, int>::type;  // shared memory: 32-bit indices
+    uint32_t s32[RB][2][NARR];
+    unsigned long long s64[RB][2][NARR];
 #pragma unroll
     for (int b = 0; b < RB; ++b)
 #pragma unroll
-        for (int a = 0; a < NARR; ++a) acc[b][a] = 0ull;
-
-    const uint32_t* Pa[NARR];
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
-    for (int a = 0; a < NARR; ++a) Pa[a] = P + a * plane_stride;
+            for (int a = 0; a < NARR; ++a) s32[b][q][a] = 0u, s64[b][q][a] = 0ull;
 
     const int k = p.k;
     // kernel row i touches DEM row offset dy = c - i
-    idx_t o = (idx_t)(prow + p.c) * pitch + lcx;
-#pragma unroll 2
-    for (int i = 0; i < k; ++i, o -= pitch) {
-        const int e = tab[i];
-        const int lo = (int)(short)(e & 0xffff);
-        const int hi1 = (e >> 16) + 1;
+    if constexpr (GLOBAL) {
+        // copy A of plane a at P + 2a*stride (P[j]), copy B at P + (2a+1)*stride (P[j+1]): the pair
+        // (P[j], P[j+1]) is an aligned 64-bit word of A when j is even, of B (at j-1) when j is odd.
+        const uint32_t* rowp[RB];
 #pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            const idx_t ob = o + (idx_t)b * pitch;
+        for (int b = 0; b < RB; ++b) rowp[b] = P + (int64_t)(prow + p.c + b) * pitch + lcx;
+        const int64_t down = pitch;
+#pragma unroll 1
+        for (int i = 0; i < k; ++i) {
+            const int e = tab[i];
+            const int lo = (int)(short)(e & 0xffff);
+            const int hi1 = (e >> 16) + 1;
+            // lcx is even: parity of the element index = parity of the offset
+            const int64_t offR = (hi1 & 1) ? (plane_stride + hi1 - 1) : (int64_t)hi1;
+            const int64_t offL = (lo & 1) ? (plane_stride + lo - 1) : (int64_t)lo;
 #pragma unroll
-            for (int a = 0; a < NARR; ++a) {
-                uint32_t hi_v, lo_v;
-                if constexpr (GLOBAL) {
-                    hi_v = __ldg(Pa[a] + ob + hi1);
-                    lo_v = __ldg(Pa[a] + ob + lo);
-                } else {
-                    hi_v = Pa[a][ob + hi1];
-                    lo_v = Pa[a][ob + lo];
+            for (int b = 0; b < RB; ++b) {
+#pragma unroll
+                for (int a = 0; a < NARR; ++a) {
+                    const uint32_t* q = rowp[b] + 2 * a * plane_stride;
+                    const uint2 hv = __ldg(reinterpret_cast<const uint2*>(q + offR));
+                    const uint2 lv = __ldg(reinterpret_cast<const uint2*>(q + offL));
+                    if ((ACC >> a) & 1) {
+                        s32[b][0][a] += hv.x - lv.x;
+                        s32[b][1][a] += hv.y - lv.y;
+                    } else {
+                        s64[b][0][a] += (unsigned long long)(uint32_t)(hv.x - lv.x);
+                        s64[b][1][a] += (unsigned long long)(uint32_t)(hv.y - lv.y);
+                    }
                 }
-                acc[b][a] += (unsigned long long)(uint32_t)(hi_v - lo_v);
+                rowp[b] -= down;
             }
+        }
+    } else {
+        int o = (prow + p.c) * pitch + lcx;
+#pragma unroll 2
+        for (int i = 0; i < k; ++i, o -= pitch) {
+            const int e = tab[i];
+            const int lo = (int)(short)(e & 0xffff);
+            const int hi1 = (e >> 16) + 1;
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                const int ob = o + b * pitch;
+#pragma unroll
+                for (int a = 0; a < NARR; ++a) {
+                    // lanes = consecutive columns (conflict-free); the thread's second pixel is 64 columns on
+                    const uint32_t* q = P + a * plane_stride + ob;
+                    const uint32_t h0 = q[hi1], h1 = q[hi1 + kTW / 2], l0 = q[lo], l1 = q[lo + kTW / 2];
+                    if ((ACC >> a) & 1) {
+                        s32[b][0][a] += h0 - l0;
+                        s32[b][1][a] += h1 - l1;
+                    } else {
+                        s64[b][0][a] += (unsigned long long)(uint32_t)(h0 - l0);
+                        s64[b][1][a] += (unsigned long long)(uint32_t)(h1 - l1);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < RB; ++b)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int a = 0; a < NARR; ++a)
+                out[b][q][a] = ((ACC >> a) & 1) ? (unsigned long long)s32[b][q][a] : s64[b][q][a];
+}
+
+// Store the RB x 2 results of one batch.  gyb: global row of batch row 0; rows < gy_first are duplicates
+// produced by the bottom clamp and are skipped.  XS: distance between the thread's two pixels.
+template <int MODE, int XS>
+__device__ __forceinline__ void store_batch(const DiscParams& p,
+                                            const unsigned long long (&acc)[ModeTraits<MODE>::RB][2][ModeTraits<MODE>::NARR],
+                                            int gyb, int gy_first, int y_end, int x) {
+    constexpr int RB = ModeTraits<MODE>::RB;
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+        const int gy = gyb + b;
+        if (gy < gy_first || gy >= y_end) continue;
+        float* o = p.out + (int64_t)(gy - p.out_gy0) * p.ld_out + x;
+        if (XS == 1) {
+            if (x + 1 < p.nx) {
+                const float r0 = finish<MODE>(p, acc[b][0], gy, x), r1 = finish<MODE>(p, acc[b][1], gy, x + 1);
+                if ((reinterpret_cast<uintptr_t>(o) & 7) == 0)
+                    *reinterpret_cast<float2*>(o) = make_float2(r0, r1);
+                else
+                    o[0] = r0, o[1] = r1;
+            } else if (x < p.nx) {
+                o[0] = finish<MODE>(p, acc[b][0], gy, x);
+            }
+        } else {
+            if (x < p.nx) o[0] = finish<MODE>(p, acc[b][0], gy, x);
+            if (x + XS < p.nx) o[XS] = finish<MODE>(p, acc[b][1], gy, x + XS);
         }
     }
 }
 
 // ---- fused kernel --------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, int ACC>
 __global__ void __launch_bounds__(kThreads) disc_fused_kernel(const DiscParams p) {
     constexpr int NARR = ModeTraits<MODE>::NARR;
     constexpr int RB = ModeTraits<MODE>::RB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(32) unsigned char smem_raw[];
     int* tab = reinterpret_cast<int*>(smem_raw);
-    const int tab_elems = (p.k + 3) & ~3;
+    const int tab_elems = (p.k + 7) & ~7;
     uint32_t* P = reinterpret_cast<uint32_t*>(smem_raw) + tab_elems;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * kTW;
-    const int y0 = p.out_gy0 + blockIdx.y * p.TH;  // global row of the tile's first output row
-    const int R = p.TH + 2 * p.halo;
+    const int y0 = p.out_gy0 + blockIdx.y * kTH;  // global row of the tile's first output row
+    const int R = kTH + 2 * p.halo;
     const int W = p.haloL + kTW + p.halo;
     const int64_t plane_stride = (int64_t)R * p.pitch;
     const bool aligned = ((p.ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dem) & 15) == 0);
 
     build_span_table(p, tab);
     for (int r = warp; r < R; r += kThreads / 32)
-        scan_row<MODE>(p, y0 - p.halo + r, x0 - p.haloL, W, P + (int64_t)r * p.pitch, plane_stride, aligned, lane);
+        scan_row<MODE, 1>(p, y0 - p.halo + r, x0 - p.haloL, W, P + (int64_t)r * p.pitch, plane_stride, aligned, lane);
     __syncthreads();
 
-    const int tx = threadIdx.x & (kTW - 1);
-    const int yg = threadIdx.x >> 7;  // 0..1
-    const int x = x0 + tx;
-    const int rows_per_thread = p.TH >> 1;
+    const int tp = threadIdx.x & 63;  // the thread owns tile columns tp and tp + 64
+    const int yg = threadIdx.x >> 6;  // row group 0..3
+    const int x = x0 + tp;
     const int y_end = p.out_gy0 + p.out_rows;
-    for (int bt = 0; bt < rows_per_thread; bt += RB) {
-        const int ty = yg * rows_per_thread + bt;  // first tile row of this batch
+#pragma unroll 1
+    for (int bt = 0; bt < kTH / 4; bt += RB) {
+        const int ty = yg * (kTH / 4) + bt;  // first tile row of this batch
         if (y0 + ty >= y_end) break;
-        unsigned long long acc[RB][NARR];
-        span_walk<MODE, false>(p, P, plane_stride, p.pitch, tab, ty + p.halo, tx + p.haloL, acc);
-        if (x < p.nx) {
-#pragma unroll
-            for (int b = 0; b < RB; ++b) {
-                const int gy = y0 + ty + b;
-                if (gy < y_end) p.out[(int64_t)(gy - p.out_gy0) * p.ld_out + x] = finish<MODE>(p, acc[b], gy, x);
-            }
-        }
+        unsigned long long acc[RB][2][NARR];
+        span_walk<MODE, ACC, false>(p, P, plane_stride, p.pitch, tab, ty + p.halo, tp + p.haloL, acc);
+        store_batch<MODE, kTW / 2>(p, acc, y0 + ty, y0 + ty, y_end, x);
     }
 }
 
 // ---- two-pass kernels ------------------------------------------------------------------------------
-// pass 1: prefix planes for global rows [prow0, prow0 + nrows) and columns [-haloL, nx + halo)
+// pass 1: prefix planes (2 copies) for global rows [prow0, prow0 + nrows) and columns [-haloL, nx + halo)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) disc_prefix_kernel(const DiscParams p, int nrows) {
     const int lane = threadIdx.x & 31;
@@ -327,50 +409,61 @@ __global__ void __launch_bounds__(kThreads) disc_prefix_kernel(const DiscParams 
     if (row >= nrows) return;
     const bool aligned = ((p.ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dem) & 15) == 0);
     const int W = p.haloL + p.nx + p.halo;
-    scan_row<MODE>(p, p.prow0 + row, -p.haloL, W, p.planes + (int64_t)row * p.pitch, p.plane_stride, aligned, lane);
+    scan_row<MODE, 2>(p, p.prow0 + row, -p.haloL, W, p.planes + (int64_t)row * p.pitch, p.plane_stride, aligned, lane);
 }
 
 // pass 2: span walk over the global planes
-template <int MODE>
+template <int MODE, int ACC>
 __global__ void __launch_bounds__(kThreads) disc_span_kernel(const DiscParams p) {
     constexpr int NARR = ModeTraits<MODE>::NARR;
     constexpr int RB = ModeTraits<MODE>::RB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(32) unsigned char smem_raw[];
     int* tab = reinterpret_cast<int*>(smem_raw);
     build_span_table(p, tab);
     __syncthreads();
 
-    const int tx = threadIdx.x & (kTW - 1);
-    const int yg = threadIdx.x >> 7;
-    const int x = blockIdx.x * kTW + tx;
-    const int xc = x < p.nx ? x : p.nx - 1;  // clamp: keeps every address inside the planes
-    const int rows_per_thread = p.TH >> 1;
-    const int y0 = p.out_gy0 + blockIdx.y * p.TH;
+    // super-column raster: tiles of kSuperCols columns are walked top to bottom before moving right
+    int tile_x, tile_y;
+    {
+        const int id = blockIdx.x;
+        const int full = p.tiles_x / kSuperCols;
+        const int per_sc = kSuperCols * p.tiles_y;
+        if (id < full * per_sc) {
+            const int sc = id / per_sc, r = id - sc * per_sc;
+            tile_y = r / kSuperCols;
+            tile_x = sc * kSuperCols + (r - tile_y * kSuperCols);
+        } else {
+            const int r = id - full * per_sc, width = p.tiles_x - full * kSuperCols;
+            tile_y = r / width;
+            tile_x = full * kSuperCols + (r - tile_y * width);
+        }
+    }
+
+    const int tp = threadIdx.x & 63;
+    const int yg = threadIdx.x >> 6;
+    const int x = tile_x * kTW + 2 * tp;
+    int xc = x;  // clamp: keeps every address inside the planes (even, so pairs stay aligned)
+    if (xc > p.nx - 1) xc = (p.nx - 1) & ~1;
+    const int y0 = p.out_gy0 + tile_y * kTH;
     const int y_end = p.out_gy0 + p.out_rows;
-    for (int bt = 0; bt < rows_per_thread; bt += RB) {
-        const int ty = yg * rows_per_thread + bt;
-        const int gy0 = y0 + ty;
+#pragma unroll 1
+    for (int bt = 0; bt < kTH / 4; bt += RB) {
+        const int gy0 = y0 + yg * (kTH / 4) + bt;
         if (gy0 >= y_end) break;
         // clamp the batch so that all RB rows stay inside the planes (duplicates are not stored)
         int gyb = gy0;
         if (gyb + RB > y_end) gyb = y_end - RB;
         if (gyb < p.out_gy0) gyb = p.out_gy0;  // out_rows < RB: planes are padded (see host)
-        unsigned long long acc[RB][NARR];
-        span_walk<MODE, true>(p, p.planes, p.plane_stride, p.pitch, tab, gyb - p.prow0, xc + p.haloL, acc);
-        if (x < p.nx) {
-#pragma unroll
-            for (int b = 0; b < RB; ++b) {
-                const int gy = gyb + b;
-                if (gy >= gy0 && gy < y_end) p.out[(int64_t)(gy - p.out_gy0) * p.ld_out + x] = finish<MODE>(p, acc[b], gy, x);
-            }
-        }
+        unsigned long long acc[RB][2][NARR];
+        span_walk<MODE, ACC, true>(p, p.planes, p.plane_stride, p.pitch, tab, gyb - p.prow0, xc + p.haloL, acc);
+        if (x == xc) store_batch<MODE, 1>(p, acc, gyb, gy0, y_end, x);
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
 struct DiscPlan {
     DiscParams p;
-    int mode;
+    int mode, acc;
     bool fused;
     size_t smem;
     int prefix_rows;  // two-pass
@@ -394,10 +487,10 @@ static long long disc_count(int k) {
     return n;
 }
 
-constexpr size_t kSmemBudget = 200 * 1024;  // leave room for a second small CTA / static smem
+constexpr size_t kFusedSmemBudget = 101 * 1024;  // keep >= 2 CTAs per SM; larger discs go two-pass
 
-static int max_rb(int mode) { return mode == TPI_Q ? 8 : 4; }
-static int narr_of(int mode) { return mode == TPI_Q ? 1 : (mode == STD_F ? 3 : 2); }
+static int max_rb(int mode) { return (mode == TPI_Q || mode == TPI_I) ? 8 : 4; }
+static int narr_of(int mode) { return (mode == TPI_Q || mode == TPI_I) ? 1 : (mode == STD_F ? 3 : 2); }
 
 // Geometry that does not depend on the data range (used by the workspace query too).
 static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPlan& pl) {
@@ -406,20 +499,19 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
     p.out_gy0 = v->out_gy0, p.out_rows = v->out_rows;
     p.k = size, p.c = (size - 1) / 2, p.mid = size / 2, p.square = size < 5;
     p.halo = size / 2;
-    p.haloL = (p.halo + 3) & ~3;
+    p.haloL = (p.halo + 7) & ~7;
     p.excl = p.c - p.mid;
-    const int tab_bytes = ((size + 3) & ~3) * 4;
-    // fused: pick the tallest tile that fits
-    pl.fused = false;
-    for (int th : {32, 16}) {
-        if (th / 2 < rb) continue;
-        const int R = th + 2 * p.halo;
+    p.tiles_x = ceil_div(p.nx, kTW);
+    p.tiles_y = ceil_div(p.out_rows, kTH);
+    const int tab_bytes = ((size + 7) & ~7) * 4;
+    {
+        const int R = kTH + 2 * p.halo;
         const int W = p.haloL + kTW + p.halo;
-        const int pitch = ((W + 3) & ~3) + 4;
+        const int pitch = ((W + 7) & ~7) + 8;
         const size_t bytes = (size_t)tab_bytes + (size_t)R * pitch * 4 * narr;
-        if (bytes <= kSmemBudget) {
+        if (bytes <= kFusedSmemBudget) {
             pl.fused = true;
-            p.TH = th, p.pitch = pitch;
+            p.pitch = pitch;
             pl.smem = bytes;
             pl.ws_bytes = 0;
             pl.prefix_rows = 0;
@@ -427,15 +519,15 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
         }
     }
     // two-pass
-    p.TH = 32;
+    pl.fused = false;
     const int W = p.haloL + p.nx + p.halo;
-    p.pitch = ((W + 3) & ~3) + 4;
+    p.pitch = ((W + 7) & ~7) + 8;
     p.prow0 = p.out_gy0 - p.halo;
     int rows = p.out_rows + 2 * p.halo;
     if (p.out_rows < rb) rows += rb - p.out_rows;  // batch clamp may read up to RB rows from out_gy0
     pl.prefix_rows = rows;
     p.plane_stride = (int64_t)rows * p.pitch;
-    pl.ws_bytes = (size_t)p.plane_stride * 4 * narr;
+    pl.ws_bytes = (size_t)p.plane_stride * 4 * narr * 2;
     pl.smem = tab_bytes;
     return 0;
 }
@@ -456,6 +548,8 @@ static int ilog2_floor(double x) {
     return e - 1;
 }
 
+constexpr double kU32 = 4294967295.0;
+
 // Fill the data-dependent constants.  what: 0 = TPI, 1 = STD.
 static int plan_disc(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, DiscPlan& pl) {
     TOPO_CHECK(size >= 2 && size <= kMaxSize, "kernel size %d outside [2, %d]", size, kMaxSize);
@@ -465,41 +559,59 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
     // integer-part range, including the zero padding value
     const double tlo = fmin(0.0, trunc(zmin)), thi = fmax(0.0, trunc(zmax));
     const double trange = thi - tlo;
-    int mode;
+    int mode, acc = 0;
     DiscParams& p = pl.p;
     memset(&p, 0, sizeof(p));
-    if (what == 0) {
+    double vmax[3] = {0, 0, 0};  // largest value a plane element can take
+    if (what == 0 && !all_integer) {
         const double c0 = fmin(0.0, floor(zmin));
         const double range = fmax(0.0, zmax) - c0 + 1.0;
-        int S = ilog2_floor(4294967295.0 / (span * range));
+        int S = ilog2_floor(kU32 / (span * range));
         if (S > 20) S = 20;
+        // a slightly coarser scale lets the whole disc sum live in 32 bits (one IADD3 per row)
+        int S32 = ilog2_floor(kU32 / (n * range));
+        if (S32 > 20) S32 = 20;
+        if (S32 >= 13) S = S32;
         if (S >= 10) {
             mode = TPI_Q;
             p.scale = (float)ldexp(1.0, S);
             p.c0i = (int)ldexp(c0, S);
             p.inv_scale = ldexp(1.0, -S);
+            vmax[0] = ldexp(range, S);
         } else {
             mode = TPI_X;
         }
+    } else if (what == 0) {
+        mode = TPI_I;
     } else {
         mode = all_integer ? STD_I : STD_F;
     }
     if (mode != TPI_Q) {
-        TOPO_CHECK(span * (trange + 1.0) < 4294967295.0, "size %d x DEM range %.0f overflows the 32-bit span sums",
-                   size, trange);
+        TOPO_CHECK(span * (trange + 1.0) < kU32, "size %d x DEM range %.0f overflows the 32-bit span sums", size, trange);
         p.tmin = (int)tlo;
         p.cmid = (int)(tlo + floor(trange / 2.0));
+        vmax[0] = trange + 1.0;
         if (mode == STD_I || mode == STD_F) {
             const double half = floor(trange / 2.0) + 1.0;
-            TOPO_CHECK(span * half * half < 4294967295.0,
-                       "size %d x (DEM range %.0f)^2 overflows the 32-bit span sums of squares", size, trange);
+            TOPO_CHECK(span * half * half < kU32, "size %d x (DEM range %.0f)^2 overflows the 32-bit span sums of squares",
+                       size, trange);
+            vmax[1] = half * half;
         }
-        int Sf = 30 - (ilog2_floor(span) + 1);
-        if (Sf > 23) Sf = 23;
-        p.fscale = (float)ldexp(1.0, Sf);
-        p.inv_fscale = ldexp(1.0, -Sf);
+        if (mode == TPI_X || mode == STD_F) {
+            int Sf = 30 - (ilog2_floor(span) + 1);
+            if (Sf > 23) Sf = 23;
+            p.fscale = (float)ldexp(1.0, Sf);
+            p.inv_fscale = ldexp(1.0, -Sf);
+            vmax[narr_of(mode) - 1] = ldexp(2.0, Sf);
+        }
     }
+    for (int a = 0; a < narr_of(mode); ++a)
+        if (n * vmax[a] < kU32) acc |= 1 << a;
+    // instantiated accumulator layouts: none, plane 0 only, all planes
+    const int full = (1 << narr_of(mode)) - 1;
+    if (acc != full) acc &= 1;
     pl.mode = mode;
+    pl.acc = acc;
     if (plan_geometry(v, size, narr_of(mode), max_rb(mode), pl)) return -1;
     p.n = n;
     p.n_ll = (long long)n;
@@ -509,31 +621,68 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
     return 0;
 }
 
-static const char* const kFusedName[4] = {"disc_fused<TPI_Q>", "disc_fused<TPI_X>", "disc_fused<STD_I>", "disc_fused<STD_F>"};
-static const char* const kPrefixName[4] = {"disc_prefix<TPI_Q>", "disc_prefix<TPI_X>", "disc_prefix<STD_I>", "disc_prefix<STD_F>"};
-static const char* const kSpanName[4] = {"disc_span<TPI_Q>", "disc_span<TPI_X>", "disc_span<STD_I>", "disc_span<STD_F>"};
+static const char* mode_name(int mode) {
+    switch (mode) {
+        case TPI_Q: return "TPI_Q";
+        case TPI_X: return "TPI_X";
+        case TPI_I: return "TPI_I";
+        case STD_I: return "STD_I";
+        default: return "STD_F";
+    }
+}
 
-template <int MODE>
+static const char* kernel_label(const char* what, int mode, int acc) {
+    // stable storage for the profiler's kernel names
+    static char names[3][5][8][40];
+    static bool init = false;
+    static const char* kinds[3] = {"disc_fused", "disc_prefix", "disc_span"};
+    if (!init) {
+        for (int w = 0; w < 3; ++w)
+            for (int m = 0; m < 5; ++m)
+                for (int a = 0; a < 8; ++a) {
+                    if (w == 1)
+                        snprintf(names[w][m][a], sizeof(names[w][m][a]), "%s<%s>", kinds[w], mode_name(m));
+                    else
+                        snprintf(names[w][m][a], sizeof(names[w][m][a]), "%s<%s,acc%d>", kinds[w], mode_name(m), a);
+                }
+        init = true;
+    }
+    const int w = what[5] == 'f' ? 0 : (what[5] == 'p' ? 1 : 2);
+    return names[w][mode][acc & 7];
+}
+
+template <int MODE, int ACC>
 static int launch_disc(const DiscPlan& pl, cudaStream_t s) {
     const DiscParams& p = pl.p;
-    dim3 grid(ceil_div(p.nx, kTW), ceil_div(p.out_rows, p.TH));
     if (pl.fused) {
         static bool attr_set[64] = {false};
         int dev = 0;
         TOPO_CUDA(cudaGetDevice(&dev));
         if (dev < 64 && !attr_set[dev]) {
-            TOPO_CUDA(cudaFuncSetAttribute(disc_fused_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            TOPO_CUDA(cudaFuncSetAttribute(disc_fused_kernel<MODE, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)(227 * 1024)));
             attr_set[dev] = true;
         }
-        TOPO_LAUNCH(kFusedName[MODE], s, disc_fused_kernel<MODE><<<grid, kThreads, pl.smem, s>>>(p));
+        dim3 grid(p.tiles_x, p.tiles_y);
+        TOPO_LAUNCH(kernel_label("disc_fused", MODE, ACC), s, disc_fused_kernel<MODE, ACC><<<grid, kThreads, pl.smem, s>>>(p));
     } else {
         const int warps = kThreads / 32;
-        TOPO_LAUNCH(kPrefixName[MODE], s,
+        TOPO_LAUNCH(kernel_label("disc_prefix", MODE, 0), s,
                     disc_prefix_kernel<MODE><<<ceil_div(pl.prefix_rows, warps), kThreads, 0, s>>>(p, pl.prefix_rows));
-        TOPO_LAUNCH(kSpanName[MODE], s, disc_span_kernel<MODE><<<grid, kThreads, pl.smem, s>>>(p));
+        TOPO_LAUNCH(kernel_label("disc_span", MODE, ACC), s,
+                    disc_span_kernel<MODE, ACC><<<p.tiles_x * p.tiles_y, kThreads, pl.smem, s>>>(p));
     }
     return 0;
+}
+
+template <int MODE>
+static int launch_disc_acc(const DiscPlan& pl, cudaStream_t s) {
+    constexpr int FULL = (1 << ModeTraits<MODE>::NARR) - 1;
+    if (pl.acc == FULL) return launch_disc<MODE, FULL>(pl, s);
+    if constexpr (FULL != 1) {
+        if (pl.acc == 1) return launch_disc<MODE, 1>(pl, s);
+    }
+    return launch_disc<MODE, 0>(pl, s);
 }
 
 static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,
@@ -553,15 +702,17 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
     if (!pl.fused) {
         TOPO_CHECK(ws != nullptr && ws_bytes >= pl.ws_bytes, "workspace too small: need %zu bytes, got %zu",
                    pl.ws_bytes, ws_bytes);
-        TOPO_CHECK((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
+        TOPO_CHECK((reinterpret_cast<uintptr_t>(ws) & 31) == 0, "workspace must be 32-byte aligned");
+        TOPO_CHECK((long long)pl.p.tiles_x * pl.p.tiles_y < 2147483647ll, "too many tiles");
         pl.p.planes = (uint32_t*)ws;
     }
     cudaStream_t s = (cudaStream_t)stream;
     switch (pl.mode) {
-        case TPI_Q: return launch_disc<TPI_Q>(pl, s);
-        case TPI_X: return launch_disc<TPI_X>(pl, s);
-        case STD_I: return launch_disc<STD_I>(pl, s);
-        default: return launch_disc<STD_F>(pl, s);
+        case TPI_Q: return launch_disc_acc<TPI_Q>(pl, s);
+        case TPI_I: return launch_disc_acc<TPI_I>(pl, s);
+        case TPI_X: return launch_disc_acc<TPI_X>(pl, s);
+        case STD_I: return launch_disc_acc<STD_I>(pl, s);
+        default: return launch_disc_acc<STD_F>(pl, s);
     }
 }
 
@@ -573,10 +724,10 @@ extern "C" {
 
 size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what) {
     if (!v || size < 2 || size > kMaxSize) return 0;
-    // worst case over the modes `what` can select (the mode depends on the data range)
+    // worst case over the modes `what` can select (the mode depends on the data)
     size_t worst = 0;
-    const int modes_tpi[2] = {TPI_Q, TPI_X}, modes_std[2] = {STD_I, STD_F};
-    for (int m = 0; m < 2; ++m) {
+    const int modes_tpi[3] = {TPI_Q, TPI_X, TPI_I}, modes_std[3] = {STD_I, STD_F, STD_F};
+    for (int m = 0; m < 3; ++m) {
         const int mode = what == 0 ? modes_tpi[m] : modes_std[m];
         DiscPlan pl;
         memset(&pl, 0, sizeof(pl));
@@ -587,8 +738,8 @@ size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what) {
 }
 
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,
-                 double zmin, double zmax, void* ws, size_t ws_bytes, void* stream) {
-    return run_disc(dem, ld_in, out, ld_out, v, size, 0, 0, zmin, zmax, ws, ws_bytes, stream);
+                 int all_integer, double zmin, double zmax, void* ws, size_t ws_bytes, void* stream) {
+    return run_disc(dem, ld_in, out, ld_out, v, size, 0, all_integer, zmin, zmax, ws, ws_bytes, stream);
 }
 
 int topo_std_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,

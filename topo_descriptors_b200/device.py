@@ -202,7 +202,7 @@ def tpi(dem, size, out_gy0=None, out_rows=None, out=None):
     ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), 0)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
     _lib.call("topo_tpi_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
-              st["min"], st["max"], _ptr(ws), ws_bytes, _stream())
+              1 if st["nonint"] == 0 else 0, st["min"], st["max"], _ptr(ws), ws_bytes, _stream())
     return out
 
 
