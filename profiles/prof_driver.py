@@ -1,6 +1,7 @@
-"""Small driver for ncu captures: one call of selected descriptors on a 16384^2 DEM (config 4).
+"""Small driver for ncu captures and quick timings: calls of selected descriptors on a 16384^2 DEM (config 4).
 
-    python profiles/prof_driver.py tpi:801 std:801 grad:801 tpi:5 grad:5
+    python profiles/prof_driver.py tpi:801 std:801 grad:801 tpi:5 grad:5          # one call each (for ncu)
+    PROF_TIME=1 python profiles/prof_driver.py tpi:801 std:801                      # 3 calls each, prints the last ms
 """
 import os
 import sys
@@ -15,14 +16,17 @@ from topo_descriptors_b200 import device as dev  # noqa: E402
 from topo_descriptors_b200.device import DeviceDEM  # noqa: E402
 
 n = int(os.environ.get("PROF_SIZE", 16384))
+timing = bool(os.environ.get("PROF_TIME"))
 core = torch.from_numpy(make_dem_rows(n, n, 0, n)).cuda()
+if os.environ.get("PROF_FLOAT"):
+    core = core + 0.25
 d = DeviceDEM(core)
 _ = d.stats
 rx = torch.full((n,), RES_M, dtype=torch.float64, device="cuda")
 ry = torch.full((n,), -RES_M, dtype=torch.float64, device="cuda")
-for spec in sys.argv[1:]:
-    kind, size = spec.split(":")
-    size = int(size)
+
+
+def run_one(kind, size):
     if kind == "tpi":
         dev.tpi(d, size)
     elif kind == "std":
@@ -32,5 +36,20 @@ for spec in sys.argv[1:]:
     elif kind == "grad":
         g = DeviceDEM(dev.gauss(d, size / 4.0, size / 4.0))
         dev.gradient_from_smooth(g, g, rx, 0, ry, 0)
-    torch.cuda.synchronize()
+    elif kind == "sobel":
+        dev.sobel_gradient(d, rx, 0, ry, 0)
+
+
+for spec in sys.argv[1:]:
+    kind, size = spec.split(":")
+    size = int(size)
+    reps = 3 if timing else 1
+    for rep in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_one(kind, size)
+        e1.record()
+        torch.cuda.synchronize()
+        if timing and rep == reps - 1:
+            print(f"{spec}: {e0.elapsed_time(e1):.3f} ms", flush=True)
 print("done")

@@ -26,6 +26,7 @@
 //              through L1/L2 with LDG.64 (measured 29.9 words/clk/SM vs 19.5 for LDG.32).  CTAs are
 //              rasterised in 16-tile-wide super-columns so that the rows in flight stay L2-resident.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -58,7 +59,12 @@ constexpr int kSuperCols = 16;  // two-pass raster: tiles per super-column
 struct DiscParams {
     const float* dem;
     float* out;
-    uint32_t* planes;  // two-pass: global prefix planes (2 copies per plane); fused: unused
+    uint32_t* planes;  // two-pass: global row-prefix planes (2 copies per plane); fused: unused
+    uint32_t* cplanes;  // hybrid: column-prefix planes (2 copies per plane), prefix_rows + 1 rows each
+    unsigned long long* sat;  // hybrid: summed-area planes (64-bit), prefix_rows + 1 rows each
+    int64_t cplane_stride, sat_stride;  // elements between consecutive copies / planes
+    int asq;     // hybrid: half-side of the square inscribed in the disc, floor(mid / sqrt(2))
+    int nrows;   // two-pass: rows of the prefix planes
     int64_t ld_in, ld_out;
     int64_t plane_stride;  // elements between consecutive plane copies
     int nx, gny, in_gy0, in_rows, out_gy0, out_rows;
@@ -148,16 +154,18 @@ __device__ __forceinline__ float4 load4_zero(const DiscParams& p, int gy, int x,
     return r;
 }
 
-// One warp scans one row: W elements starting at global column xs (multiple of 8) into the exclusive
-// prefix dstA[a][0..W] of each plane a (rows have `pitch` >= W + 8 elements, 32-byte aligned).  With
+// One warp scans one row: W elements starting at global column xs (multiple of 4) into the exclusive
+// prefix dst[a][0..W] of each plane a (rows have `pitch` >= W + 8 elements, 32-byte aligned).  With
 // COPIES == 2 the shifted copy dstB[a][k] = P[k+1] is written too.  8 elements per lane and chunk.
+// r64 != nullptr: the un-wrapped 64-bit row prefix is stored as well (input of the summed-area table).
 template <int MODE, int COPIES>
 __device__ __forceinline__ void scan_row(const DiscParams& p, int gy, int xs, int W, uint32_t* dst,
-                                         int64_t plane_stride, bool aligned, int lane) {
+                                         int64_t plane_stride, bool aligned, int lane,
+                                         unsigned long long* r64 = nullptr, int64_t r64_stride = 0) {
     constexpr int NARR = ModeTraits<MODE>::NARR;
-    uint32_t carry[NARR];
+    unsigned long long carry[NARR];
 #pragma unroll
-    for (int a = 0; a < NARR; ++a) carry[a] = 0u;
+    for (int a = 0; a < NARR; ++a) carry[a] = 0ull;
     const int nchunks = (W + 255) >> 8;
     for (int ch = 0; ch < nchunks; ++ch) {
         const int lc = (ch << 8) + (lane << 3);
@@ -176,10 +184,26 @@ __device__ __forceinline__ void scan_row(const DiscParams& p, int gy, int xs, in
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 run += (lc + j < W) ? v[j][a] : 0u;
-                s[j] = run;  // inclusive within the lane
+                s[j] = run;  // inclusive within the lane (8 values < 2^32)
             }
-            const uint32_t incl = warp_inclusive_scan_u32(run, lane);
-            const uint32_t base = carry[a] + incl - run;  // exclusive prefix at element lc
+            unsigned long long base64;
+            uint32_t base;
+            if (r64 != nullptr) {  // warp-uniform
+                unsigned long long incl = run;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                base64 = carry[a] + incl - run;
+                base = (uint32_t)base64;
+                carry[a] += __shfl_sync(0xffffffffu, incl, 31);
+            } else {
+                const uint32_t incl = warp_inclusive_scan_u32(run, lane);
+                base = (uint32_t)carry[a] + incl - run;  // exclusive prefix at element lc
+                base64 = base;
+                carry[a] = (uint32_t)carry[a] + __shfl_sync(0xffffffffu, incl, 31);
+            }
             if (lc < W) {
                 uint32_t* d = dst + (int64_t)(COPIES * a) * plane_stride + lc;
                 *reinterpret_cast<uint4*>(d) = make_uint4(base, base + s[0], base + s[1], base + s[2]);
@@ -189,15 +213,24 @@ __device__ __forceinline__ void scan_row(const DiscParams& p, int gy, int xs, in
                     *reinterpret_cast<uint4*>(e) = make_uint4(base + s[0], base + s[1], base + s[2], base + s[3]);
                     *reinterpret_cast<uint4*>(e + 4) = make_uint4(base + s[4], base + s[5], base + s[6], base + s[7]);
                 }
+                if (r64 != nullptr) {
+                    unsigned long long* q = r64 + a * r64_stride + lc;
+                    *reinterpret_cast<ulonglong2*>(q) = make_ulonglong2(base64, base64 + s[0]);
+                    *reinterpret_cast<ulonglong2*>(q + 2) = make_ulonglong2(base64 + s[1], base64 + s[2]);
+                    *reinterpret_cast<ulonglong2*>(q + 4) = make_ulonglong2(base64 + s[3], base64 + s[4]);
+                    *reinterpret_cast<ulonglong2*>(q + 6) = make_ulonglong2(base64 + s[5], base64 + s[6]);
+                }
             }
-            carry[a] += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
     // closing element P[W8] (W8 = W rounded up to 8): total of the row (P[W] itself when W % 8 == 0)
     if (lane == 0) {
         const int W8 = (W + 7) & ~7;
 #pragma unroll
-        for (int a = 0; a < NARR; ++a) dst[(int64_t)(COPIES * a) * plane_stride + W8] = carry[a];
+        for (int a = 0; a < NARR; ++a) {
+            dst[(int64_t)(COPIES * a) * plane_stride + W8] = (uint32_t)carry[a];
+            if (r64 != nullptr) r64[a * r64_stride + W8] = carry[a];
+        }
     }
 }
 
@@ -409,11 +442,253 @@ __global__ void __launch_bounds__(kThreads) disc_prefix_kernel(const DiscParams 
     if (row >= nrows) return;
     const bool aligned = ((p.ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dem) & 15) == 0);
     const int W = p.haloL + p.nx + p.halo;
-    scan_row<MODE, 2>(p, p.prow0 + row, -p.haloL, W, p.planes + (int64_t)row * p.pitch, p.plane_stride, aligned, lane);
+    // hybrid: the 64-bit row prefix of plane row `row` goes to row + 1 of the summed-area buffer (row 0 = 0)
+    unsigned long long* r64 = p.sat ? p.sat + (int64_t)(row + 1) * p.pitch : nullptr;
+    scan_row<MODE, 2>(p, p.prow0 + row, -p.haloL, W, p.planes + (int64_t)row * p.pitch, p.plane_stride, aligned, lane,
+                      r64, p.sat_stride);
+}
+
+// ---- hybrid decomposition (odd discs that run two-pass) ------------------------------------------------
+// disc = inscribed square [-a, a]^2 (a = floor(mid / sqrt 2))  +  top/bottom caps (rows |r| > a: row-prefix
+// spans)  +  left/right caps (columns |c| > a: column-prefix spans).  Lookups per pixel: 4 + 8 (mid - a)
+// instead of 4 mid + 2  (1.7x fewer).  Needs, besides the row-prefix planes:
+//   CP[Y][X] = sum_{i < Y} q[i][X]            uint32 wrap-around, 2 shifted copies, rows 0..nrows
+//   S [Y][X] = sum_{i < Y} sum_{j < X} q[i][j] uint64 (exact),                     rows 0..nrows
+// both built by a chunked column scan: per-chunk column totals -> scan of the totals -> apply.
+constexpr int kColChunk = 64;
+
+// element (row, 4 columns starting at col) of plane a as produced by `convert` (zero past the row width W)
+template <int MODE>
+__device__ __forceinline__ void load_q4(const DiscParams& p, int row, int col, int W, bool aligned,
+                                        uint32_t (&q)[4][ModeTraits<MODE>::NARR]) {
+    const float4 z = load4_zero(p, p.prow0 + row, col - p.haloL, aligned);
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        convert<MODE>(p, zz[j], q[j]);
+        if (col + j >= W) {
+#pragma unroll
+            for (int a = 0; a < ModeTraits<MODE>::NARR; ++a) q[j][a] = 0u;
+        }
+    }
+}
+
+// phase 1: column totals of each chunk of kColChunk rows.  grid (pitch / 4 / 256, nchunks).
+//   tot_q [a][chunk][col] (uint32)  : totals of q          -> column prefix
+//   tot_r [a][chunk][col] (uint64)  : totals of the 64-bit row prefix (rows 1.. of p.sat) -> summed-area table
+template <int MODE>
+__global__ void __launch_bounds__(256) disc_colsum_kernel(const DiscParams p, uint32_t* __restrict__ tot_q,
+                                                          unsigned long long* __restrict__ tot_r, int nchunks) {
+    constexpr int NARR = ModeTraits<MODE>::NARR;
+    const int col = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (col >= p.pitch) return;
+    const int chunk = blockIdx.y;
+    const int r0 = chunk * kColChunk, r1 = min(r0 + kColChunk, p.nrows);
+    const bool aligned = ((p.ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dem) & 15) == 0);
+    const int W = p.haloL + p.nx + p.halo;
+    uint32_t sq[4][NARR];
+    unsigned long long sr[4][NARR];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int a = 0; a < NARR; ++a) sq[j][a] = 0u, sr[j][a] = 0ull;
+    for (int r = r0; r < r1; ++r) {
+        uint32_t q[4][NARR];
+        load_q4<MODE>(p, r, col, W, aligned, q);
+#pragma unroll
+        for (int a = 0; a < NARR; ++a) {
+            const unsigned long long* s = p.sat + a * p.sat_stride + (int64_t)(r + 1) * p.pitch + col;
+            const ulonglong2 u0 = *reinterpret_cast<const ulonglong2*>(s), u1 = *reinterpret_cast<const ulonglong2*>(s + 2);
+            sr[0][a] += u0.x, sr[1][a] += u0.y, sr[2][a] += u1.x, sr[3][a] += u1.y;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sq[j][a] += q[j][a];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < NARR; ++a) {
+        const int64_t o = ((int64_t)a * nchunks + chunk) * p.pitch + col;
+        *reinterpret_cast<uint4*>(tot_q + o) = make_uint4(sq[0][a], sq[1][a], sq[2][a], sq[3][a]);
+        *reinterpret_cast<ulonglong2*>(tot_r + o) = make_ulonglong2(sr[0][a], sr[1][a]);
+        *reinterpret_cast<ulonglong2*>(tot_r + o + 2) = make_ulonglong2(sr[2][a], sr[3][a]);
+    }
+}
+
+// phase 2: exclusive scan of the chunk totals along the chunk axis (one thread per column and plane)
+__global__ void __launch_bounds__(256) disc_chunkscan_kernel(uint32_t* __restrict__ tot_q, unsigned long long* __restrict__ tot_r,
+                                                             int nchunks, int pitch, int narr) {
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col >= pitch) return;
+    for (int a = 0; a < narr; ++a) {
+        uint32_t rq = 0u;
+        unsigned long long rr = 0ull;
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t o = ((int64_t)a * nchunks + c) * pitch + col;
+            const uint32_t vq = tot_q[o];
+            const unsigned long long vr = tot_r[o];
+            tot_q[o] = rq, tot_r[o] = rr;
+            rq += vq, rr += vr;
+        }
+    }
+}
+
+// phase 3: inclusive column scan inside each chunk, offset by the scanned totals.
+//   CP row Y+1 (both copies) = sum of q rows 0..Y ;  S row Y+1 = sum of 64-bit row prefixes 0..Y (in place).
+template <int MODE>
+__global__ void __launch_bounds__(256) disc_colapply_kernel(const DiscParams p, const uint32_t* __restrict__ tot_q,
+                                                            const unsigned long long* __restrict__ tot_r, int nchunks) {
+    constexpr int NARR = ModeTraits<MODE>::NARR;
+    const int col = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (col >= p.pitch) return;
+    const int chunk = blockIdx.y;
+    const int r0 = chunk * kColChunk, r1 = min(r0 + kColChunk, p.nrows);
+    const bool aligned = ((p.ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dem) & 15) == 0);
+    const int W = p.haloL + p.nx + p.halo;
+    uint32_t sq[4][NARR];
+    unsigned long long sr[4][NARR];
+#pragma unroll
+    for (int a = 0; a < NARR; ++a) {
+        const int64_t o = ((int64_t)a * nchunks + chunk) * p.pitch + col;
+        const uint4 t = *reinterpret_cast<const uint4*>(tot_q + o);
+        sq[0][a] = t.x, sq[1][a] = t.y, sq[2][a] = t.z, sq[3][a] = t.w;
+        const ulonglong2 u0 = *reinterpret_cast<const ulonglong2*>(tot_r + o), u1 = *reinterpret_cast<const ulonglong2*>(tot_r + o + 2);
+        sr[0][a] = u0.x, sr[1][a] = u0.y, sr[2][a] = u1.x, sr[3][a] = u1.y;
+        if (chunk == 0) {  // row 0 of CP and S is the empty sum
+            uint32_t* cA = p.cplanes + (int64_t)(2 * a) * p.cplane_stride + col;
+            *reinterpret_cast<uint4*>(cA) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(cA + p.cplane_stride) = make_uint4(0u, 0u, 0u, 0u);
+            unsigned long long* s = p.sat + a * p.sat_stride + col;
+            *reinterpret_cast<ulonglong2*>(s) = make_ulonglong2(0ull, 0ull);
+            *reinterpret_cast<ulonglong2*>(s + 2) = make_ulonglong2(0ull, 0ull);
+        }
+    }
+    for (int r = r0; r < r1; ++r) {
+        uint32_t q[4][NARR];
+        load_q4<MODE>(p, r, col, W, aligned, q);
+#pragma unroll
+        for (int a = 0; a < NARR; ++a) {
+            unsigned long long* s = p.sat + a * p.sat_stride + (int64_t)(r + 1) * p.pitch + col;
+            const ulonglong2 u0 = *reinterpret_cast<const ulonglong2*>(s), u1 = *reinterpret_cast<const ulonglong2*>(s + 2);
+            sr[0][a] += u0.x, sr[1][a] += u0.y, sr[2][a] += u1.x, sr[3][a] += u1.y;
+            *reinterpret_cast<ulonglong2*>(s) = make_ulonglong2(sr[0][a], sr[1][a]);
+            *reinterpret_cast<ulonglong2*>(s + 2) = make_ulonglong2(sr[2][a], sr[3][a]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sq[j][a] += q[j][a];
+            uint32_t* cA = p.cplanes + (int64_t)(2 * a) * p.cplane_stride + (int64_t)(r + 1) * p.pitch + col;
+            *reinterpret_cast<uint4*>(cA) = make_uint4(sq[0][a], sq[1][a], sq[2][a], sq[3][a]);
+            // shifted copy: B[X] = A[X + 1]
+            uint32_t* cB = cA + p.cplane_stride;
+            if (col > 0) cB[-1] = sq[0][a];
+            cB[0] = sq[1][a], cB[1] = sq[2][a], cB[2] = sq[3][a];
+        }
+    }
+}
+
+// Hybrid span walk: RB rows x 2 adjacent pixels, all lookups are aligned 64-bit pairs from the A/B copies.
+template <int MODE, int ACC>
+__device__ __forceinline__ void span_walk_hybrid(const DiscParams& p, const int* __restrict__ tab, int prow, int lcx,
+                                                 unsigned long long (&out)[ModeTraits<MODE>::RB][2][ModeTraits<MODE>::NARR]) {
+    constexpr int NARR = ModeTraits<MODE>::NARR;
+    constexpr int RB = ModeTraits<MODE>::RB;
+    uint32_t s32[RB][2][NARR];
+    unsigned long long s64[RB][2][NARR];
+    const int a_sq = p.asq, mid = p.mid, pitch = p.pitch;
+
+    // ---- inscribed square from the 64-bit summed-area table: rows [py-a, py+a], columns [lcx-a, lcx+a] (+1)
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+#pragma unroll
+        for (int a = 0; a < NARR; ++a) {
+            const unsigned long long* S = p.sat + a * p.sat_stride;
+            const unsigned long long* top = S + (int64_t)(prow + b - a_sq) * pitch + lcx;       // S row py-a
+            const unsigned long long* bot = S + (int64_t)(prow + b + a_sq + 1) * pitch + lcx;   // S row py+a+1
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const unsigned long long v = __ldg(bot + q + a_sq + 1) - __ldg(top + q + a_sq + 1) - __ldg(bot + q - a_sq) +
+                                             __ldg(top + q - a_sq);
+                s32[b][q][a] = (uint32_t)v;
+                s64[b][q][a] = v;
+            }
+        }
+    }
+
+    // ---- top / bottom caps: kernel rows i with |i - mid| > a, row-prefix spans (same walk as the full disc)
+    {
+        const uint32_t* rowp[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) rowp[b] = p.planes + (int64_t)(prow + p.c + b) * pitch + lcx;
+        const int ncap = mid - a_sq;  // rows per cap
+#pragma unroll 1
+        for (int ii = 0; ii < 2 * ncap; ++ii) {
+            const int i = ii < ncap ? ii : ii + 2 * a_sq + 1;
+            const int e = tab[i];
+            const int lo = (int)(short)(e & 0xffff);
+            const int hi1 = (e >> 16) + 1;
+            const int64_t offR = ((hi1 & 1) ? (p.plane_stride + hi1 - 1) : (int64_t)hi1) - (int64_t)i * pitch;
+            const int64_t offL = ((lo & 1) ? (p.plane_stride + lo - 1) : (int64_t)lo) - (int64_t)i * pitch;
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+#pragma unroll
+                for (int a = 0; a < NARR; ++a) {
+                    const uint32_t* q = rowp[b] + 2 * a * p.plane_stride;
+                    const uint2 hv = __ldg(reinterpret_cast<const uint2*>(q + offR));
+                    const uint2 lv = __ldg(reinterpret_cast<const uint2*>(q + offL));
+                    if ((ACC >> a) & 1) {
+                        s32[b][0][a] += hv.x - lv.x;
+                        s32[b][1][a] += hv.y - lv.y;
+                    } else {
+                        s64[b][0][a] += (unsigned long long)(uint32_t)(hv.x - lv.x);
+                        s64[b][1][a] += (unsigned long long)(uint32_t)(hv.y - lv.y);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- left / right caps: columns |cc| > a, column-prefix spans of half-height h = half-width of row mid+cc
+    {
+        const uint32_t* colp[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) colp[b] = p.cplanes + (int64_t)(prow + b) * pitch + lcx;
+#pragma unroll 1
+        for (int cc = a_sq + 1; cc <= mid; ++cc) {
+            const int h = tab[mid + cc] >> 16;  // dxhi of kernel row mid+cc = its half-width (odd size)
+            // CP row (py + h + 1) minus CP row (py - h), at columns lcx +- cc (pair: +0, +1)
+            const int64_t up = -(int64_t)h * pitch, dn = (int64_t)(h + 1) * pitch;
+#pragma unroll
+            for (int sgn = 0; sgn < 2; ++sgn) {
+                const int c = sgn ? cc : -cc;
+                // lcx is even: parity of the column index = parity of c
+                const int64_t oc = (c & 1) ? (p.cplane_stride + c - 1) : (int64_t)c;
+#pragma unroll
+                for (int b = 0; b < RB; ++b) {
+#pragma unroll
+                    for (int a = 0; a < NARR; ++a) {
+                        const uint32_t* q = colp[b] + 2 * a * p.cplane_stride + oc;
+                        const uint2 hv = __ldg(reinterpret_cast<const uint2*>(q + dn));
+                        const uint2 lv = __ldg(reinterpret_cast<const uint2*>(q + up));
+                        if ((ACC >> a) & 1) {
+                            s32[b][0][a] += hv.x - lv.x;
+                            s32[b][1][a] += hv.y - lv.y;
+                        } else {
+                            s64[b][0][a] += (unsigned long long)(uint32_t)(hv.x - lv.x);
+                            s64[b][1][a] += (unsigned long long)(uint32_t)(hv.y - lv.y);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < RB; ++b)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int a = 0; a < NARR; ++a)
+                out[b][q][a] = ((ACC >> a) & 1) ? (unsigned long long)s32[b][q][a] : s64[b][q][a];
 }
 
 // pass 2: span walk over the global planes
-template <int MODE, int ACC>
+template <int MODE, int ACC, bool HYBRID>
 __global__ void __launch_bounds__(kThreads) disc_span_kernel(const DiscParams p) {
     constexpr int NARR = ModeTraits<MODE>::NARR;
     constexpr int RB = ModeTraits<MODE>::RB;
@@ -455,7 +730,10 @@ __global__ void __launch_bounds__(kThreads) disc_span_kernel(const DiscParams p)
         if (gyb + RB > y_end) gyb = y_end - RB;
         if (gyb < p.out_gy0) gyb = p.out_gy0;  // out_rows < RB: planes are padded (see host)
         unsigned long long acc[RB][2][NARR];
-        span_walk<MODE, ACC, true>(p, p.planes, p.plane_stride, p.pitch, tab, gyb - p.prow0, xc + p.haloL, acc);
+        if constexpr (HYBRID)
+            span_walk_hybrid<MODE, ACC>(p, tab, gyb - p.prow0, xc + p.haloL, acc);
+        else
+            span_walk<MODE, ACC, true>(p, p.planes, p.plane_stride, p.pitch, tab, gyb - p.prow0, xc + p.haloL, acc);
         if (x == xc) store_batch<MODE, 1>(p, acc, gyb, gy0, y_end, x);
     }
 }
@@ -464,9 +742,12 @@ __global__ void __launch_bounds__(kThreads) disc_span_kernel(const DiscParams p)
 struct DiscPlan {
     DiscParams p;
     int mode, acc;
-    bool fused;
+    bool fused, hybrid;
     size_t smem;
     int prefix_rows;  // two-pass
+    int nchunks;      // hybrid: column-scan chunks
+    // workspace layout (byte offsets)
+    size_t off_cp, off_sat, off_totq, off_totr;
     size_t ws_bytes;
 };
 
@@ -511,6 +792,7 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
         const size_t bytes = (size_t)tab_bytes + (size_t)R * pitch * 4 * narr;
         if (bytes <= kFusedSmemBudget) {
             pl.fused = true;
+            pl.hybrid = false;
             p.pitch = pitch;
             pl.smem = bytes;
             pl.ws_bytes = 0;
@@ -526,9 +808,30 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
     int rows = p.out_rows + 2 * p.halo;
     if (p.out_rows < rb) rows += rb - p.out_rows;  // batch clamp may read up to RB rows from out_gy0
     pl.prefix_rows = rows;
+    p.nrows = rows;
     p.plane_stride = (int64_t)rows * p.pitch;
-    pl.ws_bytes = (size_t)p.plane_stride * 4 * narr * 2;
+    size_t bytes = (size_t)p.plane_stride * 4 * narr * 2;
     pl.smem = tab_bytes;
+    // hybrid decomposition for odd discs: square + row caps + column caps
+    pl.hybrid = (size & 1) && !p.square;
+    if (pl.hybrid) {
+        p.asq = (int)floor((double)p.mid / sqrt(2.0));
+        while (2ll * p.asq * p.asq > (long long)p.mid * p.mid) --p.asq;
+        while (2ll * (p.asq + 1) * (p.asq + 1) <= (long long)p.mid * p.mid) ++p.asq;
+        pl.nchunks = ceil_div(rows, kColChunk);
+        p.cplane_stride = (int64_t)(rows + 1) * p.pitch;
+        p.sat_stride = (int64_t)(rows + 1) * p.pitch;
+        auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        pl.off_cp = align(bytes);
+        bytes = pl.off_cp + (size_t)p.cplane_stride * 4 * narr * 2;
+        pl.off_sat = align(bytes);
+        bytes = pl.off_sat + (size_t)p.sat_stride * 8 * narr;
+        pl.off_totq = align(bytes);
+        bytes = pl.off_totq + (size_t)narr * pl.nchunks * p.pitch * 4;
+        pl.off_totr = align(bytes);
+        bytes = pl.off_totr + (size_t)narr * pl.nchunks * p.pitch * 8;
+    }
+    pl.ws_bytes = bytes;
     return 0;
 }
 
@@ -633,11 +936,11 @@ static const char* mode_name(int mode) {
 
 static const char* kernel_label(const char* what, int mode, int acc) {
     // stable storage for the profiler's kernel names
-    static char names[3][5][8][40];
+    static char names[4][5][8][40];
     static bool init = false;
-    static const char* kinds[3] = {"disc_fused", "disc_prefix", "disc_span"};
+    static const char* kinds[4] = {"disc_fused", "disc_prefix", "disc_span", "disc_hybrid"};
     if (!init) {
-        for (int w = 0; w < 3; ++w)
+        for (int w = 0; w < 4; ++w)
             for (int m = 0; m < 5; ++m)
                 for (int a = 0; a < 8; ++a) {
                     if (w == 1)
@@ -647,8 +950,24 @@ static const char* kernel_label(const char* what, int mode, int acc) {
                 }
         init = true;
     }
-    const int w = what[5] == 'f' ? 0 : (what[5] == 'p' ? 1 : 2);
+    const int w = what[5] == 'f' ? 0 : (what[5] == 'p' ? 1 : (what[5] == 's' ? 2 : 3));
     return names[w][mode][acc & 7];
+}
+
+// Tuning knobs for the gather kernels (environment, read once): the L1 / shared-memory split and an
+// occupancy limiter.  TOPO_SPAN_CARVEOUT = preferred shared-memory carve-out in percent (default 0: the gather
+// kernels live off L1), TOPO_SPAN_EXTRA_SMEM = extra dynamic shared memory per CTA in bytes.
+static size_t span_extra_smem() {
+    static const size_t v = getenv("TOPO_SPAN_EXTRA_SMEM") ? (size_t)atol(getenv("TOPO_SPAN_EXTRA_SMEM")) : 0;
+    return v;
+}
+
+template <int MODE, int ACC, bool HYBRID>
+static int span_carveout() {
+    const int pct = getenv("TOPO_SPAN_CARVEOUT") ? atoi(getenv("TOPO_SPAN_CARVEOUT")) : 0;
+    cudaFuncSetAttribute(disc_span_kernel<MODE, ACC, HYBRID>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(disc_span_kernel<MODE, ACC, HYBRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return pct;
 }
 
 template <int MODE, int ACC>
@@ -665,12 +984,30 @@ static int launch_disc(const DiscPlan& pl, cudaStream_t s) {
         }
         dim3 grid(p.tiles_x, p.tiles_y);
         TOPO_LAUNCH(kernel_label("disc_fused", MODE, ACC), s, disc_fused_kernel<MODE, ACC><<<grid, kThreads, pl.smem, s>>>(p));
+        return 0;
+    }
+    const int warps = kThreads / 32;
+    TOPO_LAUNCH(kernel_label("disc_prefix", MODE, 0), s,
+                disc_prefix_kernel<MODE><<<ceil_div(pl.prefix_rows, warps), kThreads, 0, s>>>(p, pl.prefix_rows));
+    if (pl.hybrid) {
+        unsigned char* ws = reinterpret_cast<unsigned char*>(p.planes);
+        uint32_t* tot_q = reinterpret_cast<uint32_t*>(ws + pl.off_totq);
+        unsigned long long* tot_r = reinterpret_cast<unsigned long long*>(ws + pl.off_totr);
+        dim3 cgrid(ceil_div(p.pitch / 4, 256), pl.nchunks);
+        TOPO_LAUNCH("disc_colsum", s, disc_colsum_kernel<MODE><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
+        TOPO_LAUNCH("disc_chunkscan", s,
+                    disc_chunkscan_kernel<<<ceil_div(p.pitch, 256), 256, 0, s>>>(tot_q, tot_r, pl.nchunks, p.pitch,
+                                                                                    ModeTraits<MODE>::NARR));
+        TOPO_LAUNCH("disc_colapply", s, disc_colapply_kernel<MODE><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
+        static const int carve = span_carveout<MODE, ACC, true>();
+        (void)carve;
+        TOPO_LAUNCH(kernel_label("disc_hybrid", MODE, ACC), s,
+                    disc_span_kernel<MODE, ACC, true><<<p.tiles_x * p.tiles_y, kThreads, pl.smem + span_extra_smem(), s>>>(p));
     } else {
-        const int warps = kThreads / 32;
-        TOPO_LAUNCH(kernel_label("disc_prefix", MODE, 0), s,
-                    disc_prefix_kernel<MODE><<<ceil_div(pl.prefix_rows, warps), kThreads, 0, s>>>(p, pl.prefix_rows));
+        static const int carve = span_carveout<MODE, ACC, false>();
+        (void)carve;
         TOPO_LAUNCH(kernel_label("disc_span", MODE, ACC), s,
-                    disc_span_kernel<MODE, ACC><<<p.tiles_x * p.tiles_y, kThreads, pl.smem, s>>>(p));
+                    disc_span_kernel<MODE, ACC, false><<<p.tiles_x * p.tiles_y, kThreads, pl.smem + span_extra_smem(), s>>>(p));
     }
     return 0;
 }
@@ -705,6 +1042,10 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
         TOPO_CHECK((reinterpret_cast<uintptr_t>(ws) & 31) == 0, "workspace must be 32-byte aligned");
         TOPO_CHECK((long long)pl.p.tiles_x * pl.p.tiles_y < 2147483647ll, "too many tiles");
         pl.p.planes = (uint32_t*)ws;
+        if (pl.hybrid) {
+            pl.p.cplanes = reinterpret_cast<uint32_t*>((unsigned char*)ws + pl.off_cp);
+            pl.p.sat = reinterpret_cast<unsigned long long*>((unsigned char*)ws + pl.off_sat);
+        }
     }
     cudaStream_t s = (cudaStream_t)stream;
     switch (pl.mode) {
