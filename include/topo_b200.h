@@ -82,12 +82,16 @@ int topo_stamp_f32(float* out, int64_t ld, const int* rows, const int* cols, int
  * Small sizes run fused (tile + halo prefix in shared memory); larger sizes run two passes through
  * `ws` (prefix planes in HBM, gathered with 64-bit loads). */
 size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi, 1 std*/);
+/* tpi(size) and std(size) of an integer-valued DEM both need the disc sums of trunc(z): when this returns 1
+ * the first call can keep them (tsum_op = 1, tsum = out_rows*nx uint64 on the DEVICE) and the second reuse
+ * them (tsum_op = 2), which removes one of the three gather passes of a tpi+std pair.  tsum_op = 0: off. */
+int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer);
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
-                 int size, int all_integer, double zmin, double zmax, void* ws, size_t ws_bytes,
-                 void* stream);
+                 int size, int all_integer, double zmin, double zmax, unsigned long long* tsum,
+                 int tsum_op, void* ws, size_t ws_bytes, void* stream);
 int topo_std_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
-                 int size, int all_integer, double zmin, double zmax, void* ws,
-                 size_t ws_bytes, void* stream);
+                 int size, int all_integer, double zmin, double zmax, unsigned long long* tsum,
+                 int tsum_op, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Gaussian smoothing (topo.py:62-80; scipy.ndimage.gaussian_filter semantics) -------------
  * Separable, radius int(4*sigma+0.5), float64 weights and accumulation, axis 0 then axis 1 with a

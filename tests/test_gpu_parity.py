@@ -160,6 +160,24 @@ def test_std_two_pass_and_flat():
     assert maxdiff(topo.std(zneg, 9), O.std_exact(zneg, 9)) <= TOL_M
 
 
+def test_tpi_std_share_disc_sums():
+    """tpi(size) + std(size) on an integer DEM share the T-plane disc sums: identical to the unshared calls."""
+    zi = fractal_dem(420, 500, seed=14, integer=True)
+    d = DeviceDEM(dev.to_device(zi))
+    for size in (151, 201):
+        t_ref = dev.tpi(d, size, share=False)
+        s_ref = dev.std(d, size, share=False)
+        t1 = dev.tpi(d, size)            # computes and keeps the sums
+        assert d._tsum is not None
+        s1 = dev.std(d, size)            # reuses them
+        assert d._tsum is None
+        s2 = dev.std(d, size)            # nothing cached: computes (and keeps) again
+        t2 = dev.tpi(d, size)            # reuses
+        for a, b in ((t1, t_ref), (t2, t_ref), (s1, s_ref), (s2, s_ref)):
+            assert bool((a == b).all())
+        assert maxdiff(s1.cpu().numpy(), O.std_exact(zi, size)) <= TOL_M
+
+
 def test_std_sigma(golden):
     got = topo.std(golden["in__zc"], 7, sigma=1.75)
     assert maxdiff(got, O.std_exact(golden["in__zc"], 7, sigma=1.75)) <= TOL_M

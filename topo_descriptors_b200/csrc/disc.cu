@@ -35,7 +35,8 @@
 
 namespace topo {
 
-enum DiscMode { TPI_Q = 0, TPI_X = 1, STD_I = 2, STD_F = 3, TPI_I = 4 };
+// PL_*: single planes, used by the two-pass path which processes one plane per launch
+enum DiscMode { TPI_Q = 0, TPI_X = 1, STD_I = 2, STD_F = 3, TPI_I = 4, PL_T = 5, PL_Q = 6, PL_F = 7 };
 
 template <int MODE>
 struct ModeTraits;
@@ -49,6 +50,12 @@ template <>
 struct ModeTraits<STD_I> { static constexpr int NARR = 2; static constexpr int RB = 4; };
 template <>
 struct ModeTraits<STD_F> { static constexpr int NARR = 3; static constexpr int RB = 4; };
+template <>
+struct ModeTraits<PL_T> { static constexpr int NARR = 1; static constexpr int RB = 8; };
+template <>
+struct ModeTraits<PL_Q> { static constexpr int NARR = 1; static constexpr int RB = 8; };
+template <>
+struct ModeTraits<PL_F> { static constexpr int NARR = 1; static constexpr int RB = 8; };
 
 constexpr int kTW = 128;        // output tile width: 64 threads x 2 pixels
 constexpr int kTH = 32;         // output tile height: 4 row groups x 8 rows
@@ -64,6 +71,10 @@ struct DiscParams {
     unsigned long long* sat;  // hybrid: summed-area planes (64-bit), prefix_rows + 1 rows each
     int64_t cplane_stride, sat_stride;  // elements between consecutive copies / planes
     int asq;     // hybrid: half-side of the square inscribed in the disc, floor(mid / sqrt(2))
+    int dbg_skip;  // profiling only (TOPO_DBG_SKIP): 1 = skip column caps, 2 = skip row caps, 4 = skip square
+    unsigned long long* partial;  // two-pass, multi-plane modes: raw disc sums, [plane][out_rows][nx]
+    int64_t partial_stride;
+    unsigned long long* tsum;  // optional: raw sums of the T plane (trunc(z) - tmin), shared between tpi and std
     int nrows;   // two-pass: rows of the prefix planes
     int64_t ld_in, ld_out;
     int64_t plane_stride;  // elements between consecutive plane copies
@@ -125,6 +136,12 @@ template <int MODE>
 __device__ __forceinline__ void convert(const DiscParams& p, float z, uint32_t (&v)[ModeTraits<MODE>::NARR]) {
     if constexpr (MODE == TPI_Q) {
         v[0] = (uint32_t)(__float2int_rn(z * p.scale) - p.c0i);
+    } else if constexpr (MODE == PL_Q) {
+        const int d = __float2int_rz(z) - p.cmid;
+        v[0] = (uint32_t)(d * d);
+    } else if constexpr (MODE == PL_F) {
+        const float f1 = (z - (float)__float2int_rz(z)) + 1.0f;
+        v[0] = (uint32_t)__float2int_rn(f1 * p.fscale);
     } else {
         const int t = __float2int_rz(z);
         v[0] = (uint32_t)(t - p.tmin);
@@ -583,115 +600,129 @@ __global__ void __launch_bounds__(256) disc_colapply_kernel(const DiscParams p, 
     }
 }
 
-// Hybrid span walk: RB rows x 2 adjacent pixels, all lookups are aligned 64-bit pairs from the A/B copies.
-template <int MODE, int ACC>
-__device__ __forceinline__ void span_walk_hybrid(const DiscParams& p, const int* __restrict__ tab, int prow, int lcx,
-                                                 unsigned long long (&out)[ModeTraits<MODE>::RB][2][ModeTraits<MODE>::NARR]) {
-    constexpr int NARR = ModeTraits<MODE>::NARR;
-    constexpr int RB = ModeTraits<MODE>::RB;
-    uint32_t s32[RB][2][NARR];
-    unsigned long long s64[RB][2][NARR];
-    const int a_sq = p.asq, mid = p.mid, pitch = p.pitch;
+// ---- two-pass span kernels: ONE plane per launch, 8 rows x 2 adjacent pixels per thread -----------------------
+// All lookups are aligned 64-bit pairs (P[j], P[j+1]) from the A/B copies.  Accumulators are 32-bit when the
+// whole disc sum of the plane fits (ACC32), else 64-bit.
+constexpr int kRB = 8;
 
-    // ---- inscribed square from the 64-bit summed-area table: rows [py-a, py+a], columns [lcx-a, lcx+a] (+1)
-#pragma unroll
-    for (int b = 0; b < RB; ++b) {
-#pragma unroll
-        for (int a = 0; a < NARR; ++a) {
-            const unsigned long long* S = p.sat + a * p.sat_stride;
-            const unsigned long long* top = S + (int64_t)(prow + b - a_sq) * pitch + lcx;       // S row py-a
-            const unsigned long long* bot = S + (int64_t)(prow + b + a_sq + 1) * pitch + lcx;   // S row py+a+1
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const unsigned long long v = __ldg(bot + q + a_sq + 1) - __ldg(top + q + a_sq + 1) - __ldg(bot + q - a_sq) +
-                                             __ldg(top + q - a_sq);
-                s32[b][q][a] = (uint32_t)v;
-                s64[b][q][a] = v;
-            }
-        }
+struct PairAcc {
+    uint32_t s32[kRB][2];
+    unsigned long long s64[kRB][2];
+};
+
+template <bool ACC32>
+__device__ __forceinline__ void pair_add(PairAcc& A, int b, const uint2 hv, const uint2 lv) {
+    if (ACC32) {
+        A.s32[b][0] += hv.x - lv.x;
+        A.s32[b][1] += hv.y - lv.y;
+    } else {
+        A.s64[b][0] += (unsigned long long)(uint32_t)(hv.x - lv.x);
+        A.s64[b][1] += (unsigned long long)(uint32_t)(hv.y - lv.y);
     }
+}
 
-    // ---- top / bottom caps: kernel rows i with |i - mid| > a, row-prefix spans (same walk as the full disc)
-    {
-        const uint32_t* rowp[RB];
-#pragma unroll
-        for (int b = 0; b < RB; ++b) rowp[b] = p.planes + (int64_t)(prow + p.c + b) * pitch + lcx;
-        const int ncap = mid - a_sq;  // rows per cap
-#pragma unroll 1
-        for (int ii = 0; ii < 2 * ncap; ++ii) {
-            const int i = ii < ncap ? ii : ii + 2 * a_sq + 1;
+// Row-prefix spans of kernel rows [i_begin, i_end), GROUPED BY PREFIX ROW: output row b and kernel row i
+// read prefix row R0 + b - i, so for t = i - b fixed the 8 (b, i = t + b) lookups hit the SAME prefix row at
+// neighbouring columns: the 16 loads of a step share 2-4 cache lines (immediate L1 reuse, independent of
+// what the other warps stream through L1).  The offsets of i = t .. t+7 live in a rotating register window.
+// lead / lag: the row groups of a CTA (8 rows apart) start `lead` steps early and stop `lag` steps late so that
+// at every step ALL warps of the CTA read the same prefix row: its lines are fetched from L2 once per CTA
+// instead of once per row group.  Steps without any valid (b, i) slot skip their loads.
+template <bool ACC32>
+__device__ __forceinline__ void row_walk_grouped(const DiscParams& p, const int* __restrict__ tab, int R0, int lcx,
+                                                 int i_begin, int i_end, int lead, int lag, PairAcc& A) {
+    const int pitch = p.pitch;
+    const int pstride = (int)p.plane_stride;  // host guarantees it fits 31 bits
+    int offR[kRB], offL[kRB];
+    auto fetch = [&](int i, int& oR, int& oL) {
+        if (i >= i_begin && i < i_end) {
             const int e = tab[i];
             const int lo = (int)(short)(e & 0xffff);
             const int hi1 = (e >> 16) + 1;
-            const int64_t offR = ((hi1 & 1) ? (p.plane_stride + hi1 - 1) : (int64_t)hi1) - (int64_t)i * pitch;
-            const int64_t offL = ((lo & 1) ? (p.plane_stride + lo - 1) : (int64_t)lo) - (int64_t)i * pitch;
+            // lcx is even: parity of the element index = parity of the offset; odd -> shifted copy B
+            oR = (hi1 & 1) ? (pstride + hi1 - 1) : hi1;
+            oL = (lo & 1) ? (pstride + lo - 1) : lo;
+        } else {
+            oR = 0, oL = 0;  // both loads hit the same word: contributes 0
+        }
+    };
+    const int t0 = i_begin - (kRB - 1) - lead;
 #pragma unroll
-            for (int b = 0; b < RB; ++b) {
+    for (int b = 0; b < kRB; ++b) fetch(t0 + b, offR[b], offL[b]);
+    const int last_row = p.nrows - 1;
+#pragma unroll 1
+    for (int t = t0; t < i_end + lag; t += kRB) {
 #pragma unroll
-                for (int a = 0; a < NARR; ++a) {
-                    const uint32_t* q = rowp[b] + 2 * a * p.plane_stride;
-                    const uint2 hv = __ldg(reinterpret_cast<const uint2*>(q + offR));
-                    const uint2 lv = __ldg(reinterpret_cast<const uint2*>(q + offL));
-                    if ((ACC >> a) & 1) {
-                        s32[b][0][a] += hv.x - lv.x;
-                        s32[b][1][a] += hv.y - lv.y;
-                    } else {
-                        s64[b][0][a] += (unsigned long long)(uint32_t)(hv.x - lv.x);
-                        s64[b][1][a] += (unsigned long long)(uint32_t)(hv.y - lv.y);
-                    }
+        for (int s = 0; s < kRB; ++s) {
+            if (t + s + kRB > i_begin && t + s < i_end) {  // some slot i = t+s+b is valid (warp-uniform)
+                int r = R0 - (t + s);  // slots outside the range carry zero contributions: keep them in bounds
+                r = r < 0 ? 0 : (r > last_row ? last_row : r);
+                const uint32_t* rowp = p.planes + (int64_t)r * pitch + lcx;
+#pragma unroll
+                for (int b = 0; b < kRB; ++b) {
+                    const uint2 hv = __ldg(reinterpret_cast<const uint2*>(rowp + offR[b]));
+                    const uint2 lv = __ldg(reinterpret_cast<const uint2*>(rowp + offL[b]));
+                    pair_add<ACC32>(A, b, hv, lv);
                 }
             }
+#pragma unroll
+            for (int b = 0; b < kRB - 1; ++b) offR[b] = offR[b + 1], offL[b] = offL[b + 1];
+            fetch(t + s + kRB, offR[kRB - 1], offL[kRB - 1]);
         }
     }
+}
 
-    // ---- left / right caps: columns |cc| > a, column-prefix spans of half-height h = half-width of row mid+cc
-    {
-        const uint32_t* colp[RB];
+// Hybrid: inscribed square from the 64-bit summed-area table + row caps (grouped walk) + column caps.
+template <bool ACC32>
+__device__ __forceinline__ void hybrid_walk(const DiscParams& p, const int* __restrict__ tab, int prow, int lcx, int lead,
+                                            int lag, PairAcc& A) {
+    const int a_sq = p.asq, mid = p.mid, pitch = p.pitch;
+    // ---- square: rows [py-a, py+a], columns [lcx-a, lcx+a] (+1 for the second pixel)
 #pragma unroll
-        for (int b = 0; b < RB; ++b) colp[b] = p.cplanes + (int64_t)(prow + b) * pitch + lcx;
+    for (int b = 0; b < kRB; ++b) {
+        const unsigned long long* top = p.sat + (int64_t)(prow + b - a_sq) * pitch + lcx;      // S row py-a
+        const unsigned long long* bot = p.sat + (int64_t)(prow + b + a_sq + 1) * pitch + lcx;  // S row py+a+1
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const unsigned long long v = __ldg(bot + q + a_sq + 1) - __ldg(top + q + a_sq + 1) - __ldg(bot + q - a_sq) +
+                                         __ldg(top + q - a_sq);
+            A.s32[b][q] = (uint32_t)v;
+            A.s64[b][q] = v;
+        }
+    }
+    // ---- top / bottom caps: kernel rows |i - mid| > a
+    const int ncap = mid - a_sq;
+    if (!(p.dbg_skip & 2)) {
+        row_walk_grouped<ACC32>(p, tab, prow + p.c, lcx, 0, ncap, lead, lag, A);
+        row_walk_grouped<ACC32>(p, tab, prow + p.c, lcx, p.k - ncap, p.k, lead, lag, A);
+    }
+    // ---- left / right caps: columns |cc| > a, column-prefix spans of half-height h = half-width of row mid+cc
+    if (!(p.dbg_skip & 1)) {
+        const uint32_t* colp = p.cplanes + (int64_t)prow * pitch + lcx;
+        const int cstride = (int)p.cplane_stride;
 #pragma unroll 1
         for (int cc = a_sq + 1; cc <= mid; ++cc) {
             const int h = tab[mid + cc] >> 16;  // dxhi of kernel row mid+cc = its half-width (odd size)
-            // CP row (py + h + 1) minus CP row (py - h), at columns lcx +- cc (pair: +0, +1)
-            const int64_t up = -(int64_t)h * pitch, dn = (int64_t)(h + 1) * pitch;
+            const int up = -h * pitch, dn = (h + 1) * pitch;
 #pragma unroll
             for (int sgn = 0; sgn < 2; ++sgn) {
                 const int c = sgn ? cc : -cc;
-                // lcx is even: parity of the column index = parity of c
-                const int64_t oc = (c & 1) ? (p.cplane_stride + c - 1) : (int64_t)c;
+                const int oc = (c & 1) ? (cstride + c - 1) : c;  // lcx even: parity of the column = parity of c
 #pragma unroll
-                for (int b = 0; b < RB; ++b) {
-#pragma unroll
-                    for (int a = 0; a < NARR; ++a) {
-                        const uint32_t* q = colp[b] + 2 * a * p.cplane_stride + oc;
-                        const uint2 hv = __ldg(reinterpret_cast<const uint2*>(q + dn));
-                        const uint2 lv = __ldg(reinterpret_cast<const uint2*>(q + up));
-                        if ((ACC >> a) & 1) {
-                            s32[b][0][a] += hv.x - lv.x;
-                            s32[b][1][a] += hv.y - lv.y;
-                        } else {
-                            s64[b][0][a] += (unsigned long long)(uint32_t)(hv.x - lv.x);
-                            s64[b][1][a] += (unsigned long long)(uint32_t)(hv.y - lv.y);
-                        }
-                    }
+                for (int b = 0; b < kRB; ++b) {
+                    const uint32_t* q = colp + (int64_t)b * pitch + oc;
+                    const uint2 hv = __ldg(reinterpret_cast<const uint2*>(q + dn));
+                    const uint2 lv = __ldg(reinterpret_cast<const uint2*>(q + up));
+                    pair_add<ACC32>(A, b, hv, lv);
                 }
             }
         }
     }
-#pragma unroll
-    for (int b = 0; b < RB; ++b)
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int a = 0; a < NARR; ++a)
-                out[b][q][a] = ((ACC >> a) & 1) ? (unsigned long long)s32[b][q][a] : s64[b][q][a];
 }
 
-// pass 2: span walk over the global planes
-template <int MODE, int ACC, bool HYBRID>
-__global__ void __launch_bounds__(kThreads) disc_span_kernel(const DiscParams p) {
-    constexpr int NARR = ModeTraits<MODE>::NARR;
-    constexpr int RB = ModeTraits<MODE>::RB;
+// FIN: TPI_Q / TPI_I = finish in place (single-plane descriptors); -1 = store the raw sums of plane `plane`.
+template <bool ACC32, bool HYBRID, int FIN>
+__global__ void __launch_bounds__(kThreads) disc_span_kernel(const DiscParams p, int plane) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     int* tab = reinterpret_cast<int*>(smem_raw);
     build_span_table(p, tab);
@@ -721,20 +752,69 @@ __global__ void __launch_bounds__(kThreads) disc_span_kernel(const DiscParams p)
     if (xc > p.nx - 1) xc = (p.nx - 1) & ~1;
     const int y0 = p.out_gy0 + tile_y * kTH;
     const int y_end = p.out_gy0 + p.out_rows;
-#pragma unroll 1
-    for (int bt = 0; bt < kTH / 4; bt += RB) {
-        const int gy0 = y0 + yg * (kTH / 4) + bt;
-        if (gy0 >= y_end) break;
-        // clamp the batch so that all RB rows stay inside the planes (duplicates are not stored)
-        int gyb = gy0;
-        if (gyb + RB > y_end) gyb = y_end - RB;
-        if (gyb < p.out_gy0) gyb = p.out_gy0;  // out_rows < RB: planes are padded (see host)
-        unsigned long long acc[RB][2][NARR];
-        if constexpr (HYBRID)
-            span_walk_hybrid<MODE, ACC>(p, tab, gyb - p.prow0, xc + p.haloL, acc);
-        else
-            span_walk<MODE, ACC, true>(p, p.planes, p.plane_stride, p.pitch, tab, gyb - p.prow0, xc + p.haloL, acc);
-        if (x == xc) store_batch<MODE, 1>(p, acc, gyb, gy0, y_end, x);
+    const int gy0 = y0 + yg * kRB;
+    if (gy0 >= y_end) return;
+    // clamp the batch so that all rows stay inside the planes (duplicates are not stored)
+    int gyb = gy0;
+    if (gyb + kRB > y_end) gyb = y_end - kRB;
+    if (gyb < p.out_gy0) gyb = p.out_gy0;  // out_rows < 8: planes are padded (see host)
+
+    PairAcc A;
+#pragma unroll
+    for (int b = 0; b < kRB; ++b) A.s32[b][0] = A.s32[b][1] = 0u, A.s64[b][0] = A.s64[b][1] = 0ull;
+    const int prow = gyb - p.prow0, lcx = xc + p.haloL;
+    // lead / lag would put the CTA's row groups in lockstep on the same prefix row (fewer L2 fetches); measured
+    // slower on B200 (the walk is bound by L1 wavefronts, not by L2 traffic, and lockstep adds 24 steps): off.
+    const int lead = 0, lag = 0;
+    if constexpr (HYBRID)
+        hybrid_walk<ACC32>(p, tab, prow, lcx, lead, lag, A);
+    else
+        row_walk_grouped<ACC32>(p, tab, prow + p.c, lcx, 0, p.k, lead, lag, A);
+
+    if (x != xc) return;
+#pragma unroll
+    for (int b = 0; b < kRB; ++b) {
+        const int gy = gyb + b;
+        if (gy < gy0 || gy >= y_end) continue;
+        const unsigned long long v0 = ACC32 ? (unsigned long long)A.s32[b][0] : A.s64[b][0];
+        const unsigned long long v1 = ACC32 ? (unsigned long long)A.s32[b][1] : A.s64[b][1];
+        if constexpr (FIN >= 0) {
+            float* o = p.out + (int64_t)(gy - p.out_gy0) * p.ld_out + x;
+            const unsigned long long a0[1] = {v0}, a1[1] = {v1};
+            if (x + 1 < p.nx) {
+                const float r0 = finish<FIN>(p, a0, gy, x), r1 = finish<FIN>(p, a1, gy, x + 1);
+                if ((reinterpret_cast<uintptr_t>(o) & 7) == 0)
+                    *reinterpret_cast<float2*>(o) = make_float2(r0, r1);
+                else
+                    o[0] = r0, o[1] = r1;
+            } else {
+                o[0] = finish<FIN>(p, a0, gy, x);
+            }
+            if (p.tsum) {  // keep the raw T-plane sums for a following std() of the same size
+                unsigned long long* t = p.tsum + (int64_t)(gy - p.out_gy0) * p.nx + x;
+                t[0] = v0;
+                if (x + 1 < p.nx) t[1] = v1;
+            }
+        } else {
+            const int64_t idx = (int64_t)(gy - p.out_gy0) * p.nx + x;
+            unsigned long long* o = (plane == 0 && p.tsum) ? p.tsum + idx : p.partial + plane * p.partial_stride + idx;
+            o[0] = v0;
+            if (x + 1 < p.nx) o[1] = v1;
+        }
+    }
+}
+
+// Epilogue of the multi-plane modes on the two-pass path: reads the raw plane sums.
+template <int MODE>
+__global__ void __launch_bounds__(256) disc_finish_kernel(const DiscParams p) {
+    constexpr int NARR = ModeTraits<MODE>::NARR;
+    const int64_t total = (int64_t)p.out_rows * p.nx;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        const int r = (int)(idx / p.nx), x = (int)(idx - (int64_t)r * p.nx);
+        unsigned long long acc[NARR];
+#pragma unroll
+        for (int a = 0; a < NARR; ++a) acc[a] = (a == 0 && p.tsum) ? p.tsum[idx] : p.partial[a * p.partial_stride + idx];
+        p.out[(int64_t)r * p.ld_out + x] = finish<MODE>(p, acc, p.out_gy0 + r, x);
     }
 }
 
@@ -747,7 +827,7 @@ struct DiscPlan {
     int prefix_rows;  // two-pass
     int nchunks;      // hybrid: column-scan chunks
     // workspace layout (byte offsets)
-    size_t off_cp, off_sat, off_totq, off_totr;
+    size_t off_cp, off_sat, off_totq, off_totr, off_partial;
     size_t ws_bytes;
 };
 
@@ -800,17 +880,18 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
             return 0;
         }
     }
-    // two-pass
+    // two-pass: one plane per launch, the workspace is reused by the planes
     pl.fused = false;
     const int W = p.haloL + p.nx + p.halo;
     p.pitch = ((W + 7) & ~7) + 8;
     p.prow0 = p.out_gy0 - p.halo;
     int rows = p.out_rows + 2 * p.halo;
-    if (p.out_rows < rb) rows += rb - p.out_rows;  // batch clamp may read up to RB rows from out_gy0
+    if (p.out_rows < kRB) rows += kRB - p.out_rows;  // batch clamp may read up to 8 rows from out_gy0
     pl.prefix_rows = rows;
     p.nrows = rows;
     p.plane_stride = (int64_t)rows * p.pitch;
-    size_t bytes = (size_t)p.plane_stride * 4 * narr * 2;
+    auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t bytes = align((size_t)p.plane_stride * 4 * 2);
     pl.smem = tab_bytes;
     // hybrid decomposition for odd discs: square + row caps + column caps
     pl.hybrid = (size & 1) && !p.square;
@@ -821,17 +902,22 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
         pl.nchunks = ceil_div(rows, kColChunk);
         p.cplane_stride = (int64_t)(rows + 1) * p.pitch;
         p.sat_stride = (int64_t)(rows + 1) * p.pitch;
-        auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        pl.off_cp = align(bytes);
-        bytes = pl.off_cp + (size_t)p.cplane_stride * 4 * narr * 2;
-        pl.off_sat = align(bytes);
-        bytes = pl.off_sat + (size_t)p.sat_stride * 8 * narr;
-        pl.off_totq = align(bytes);
-        bytes = pl.off_totq + (size_t)narr * pl.nchunks * p.pitch * 4;
-        pl.off_totr = align(bytes);
-        bytes = pl.off_totr + (size_t)narr * pl.nchunks * p.pitch * 8;
+        pl.off_cp = bytes;
+        bytes = align(pl.off_cp + (size_t)p.cplane_stride * 4 * 2);
+        pl.off_sat = bytes;
+        bytes = align(pl.off_sat + (size_t)p.sat_stride * 8);
+        pl.off_totq = bytes;
+        bytes = align(pl.off_totq + (size_t)pl.nchunks * p.pitch * 4);
+        pl.off_totr = bytes;
+        bytes = align(pl.off_totr + (size_t)pl.nchunks * p.pitch * 8);
+    }
+    pl.off_partial = bytes;
+    if (narr > 1) {
+        p.partial_stride = (int64_t)p.out_rows * p.nx;
+        bytes += (size_t)narr * p.partial_stride * 8;
     }
     pl.ws_bytes = bytes;
+    (void)rb;
     return 0;
 }
 
@@ -910,12 +996,14 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
     }
     for (int a = 0; a < narr_of(mode); ++a)
         if (n * vmax[a] < kU32) acc |= 1 << a;
-    // instantiated accumulator layouts: none, plane 0 only, all planes
-    const int full = (1 << narr_of(mode)) - 1;
-    if (acc != full) acc &= 1;
     pl.mode = mode;
-    pl.acc = acc;
     if (plan_geometry(v, size, narr_of(mode), max_rb(mode), pl)) return -1;
+    if (pl.fused) {
+        // instantiated accumulator layouts of the fused kernels: none, plane 0 only, all planes
+        const int full = (1 << narr_of(mode)) - 1;
+        if (acc != full) acc &= 1;
+    }
+    pl.acc = acc;
     p.n = n;
     p.n_ll = (long long)n;
     p.inv_n_nm1 = 1.0 / (n * (n - 1.0));
@@ -930,100 +1018,123 @@ static const char* mode_name(int mode) {
         case TPI_X: return "TPI_X";
         case TPI_I: return "TPI_I";
         case STD_I: return "STD_I";
-        default: return "STD_F";
+        case STD_F: return "STD_F";
+        case PL_T: return "T";
+        case PL_Q: return "Q";
+        default: return "F";
     }
 }
 
-static const char* kernel_label(const char* what, int mode, int acc) {
+static const char* kernel_label(const char* kind, int mode, int acc) {
     // stable storage for the profiler's kernel names
-    static char names[4][5][8][40];
-    static bool init = false;
-    static const char* kinds[4] = {"disc_fused", "disc_prefix", "disc_span", "disc_hybrid"};
-    if (!init) {
-        for (int w = 0; w < 4; ++w)
-            for (int m = 0; m < 5; ++m)
-                for (int a = 0; a < 8; ++a) {
-                    if (w == 1)
-                        snprintf(names[w][m][a], sizeof(names[w][m][a]), "%s<%s>", kinds[w], mode_name(m));
-                    else
-                        snprintf(names[w][m][a], sizeof(names[w][m][a]), "%s<%s,acc%d>", kinds[w], mode_name(m), a);
-                }
-        init = true;
-    }
-    const int w = what[5] == 'f' ? 0 : (what[5] == 'p' ? 1 : (what[5] == 's' ? 2 : 3));
-    return names[w][mode][acc & 7];
+    static char names[64][48];
+    static int used = 0;
+    char buf[48];
+    snprintf(buf, sizeof(buf), "%s<%s,acc%d>", kind, mode_name(mode), acc);
+    for (int i = 0; i < used; ++i)
+        if (strcmp(names[i], buf) == 0) return names[i];
+    if (used == 64) return "disc";
+    strcpy(names[used], buf);
+    return names[used++];
 }
 
-// Tuning knobs for the gather kernels (environment, read once): the L1 / shared-memory split and an
-// occupancy limiter.  TOPO_SPAN_CARVEOUT = preferred shared-memory carve-out in percent (default 0: the gather
-// kernels live off L1), TOPO_SPAN_EXTRA_SMEM = extra dynamic shared memory per CTA in bytes.
+// Extra dynamic shared memory per CTA for the gather kernels (environment knob for occupancy experiments).
 static size_t span_extra_smem() {
     static const size_t v = getenv("TOPO_SPAN_EXTRA_SMEM") ? (size_t)atol(getenv("TOPO_SPAN_EXTRA_SMEM")) : 0;
     return v;
 }
 
-template <int MODE, int ACC, bool HYBRID>
-static int span_carveout() {
-    const int pct = getenv("TOPO_SPAN_CARVEOUT") ? atoi(getenv("TOPO_SPAN_CARVEOUT")) : 0;
-    cudaFuncSetAttribute(disc_span_kernel<MODE, ACC, HYBRID>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(disc_span_kernel<MODE, ACC, HYBRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    return pct;
+template <int MODE, int ACC>
+static int launch_fused(const DiscPlan& pl, cudaStream_t s) {
+    const DiscParams& p = pl.p;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    TOPO_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        TOPO_CUDA(cudaFuncSetAttribute(disc_fused_kernel<MODE, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(227 * 1024)));
+        attr_set[dev] = true;
+    }
+    dim3 grid(p.tiles_x, p.tiles_y);
+    TOPO_LAUNCH(kernel_label("disc_fused", MODE, ACC), s, disc_fused_kernel<MODE, ACC><<<grid, kThreads, pl.smem, s>>>(p));
+    return 0;
 }
 
-template <int MODE, int ACC>
-static int launch_disc(const DiscPlan& pl, cudaStream_t s) {
-    const DiscParams& p = pl.p;
-    if (pl.fused) {
-        static bool attr_set[64] = {false};
-        int dev = 0;
-        TOPO_CUDA(cudaGetDevice(&dev));
-        if (dev < 64 && !attr_set[dev]) {
-            TOPO_CUDA(cudaFuncSetAttribute(disc_fused_kernel<MODE, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(227 * 1024)));
-            attr_set[dev] = true;
-        }
-        dim3 grid(p.tiles_x, p.tiles_y);
-        TOPO_LAUNCH(kernel_label("disc_fused", MODE, ACC), s, disc_fused_kernel<MODE, ACC><<<grid, kThreads, pl.smem, s>>>(p));
-        return 0;
+template <int MODE>
+static int launch_fused_acc(const DiscPlan& pl, cudaStream_t s) {
+    constexpr int FULL = (1 << ModeTraits<MODE>::NARR) - 1;
+    if (pl.acc == FULL) return launch_fused<MODE, FULL>(pl, s);
+    if constexpr (FULL != 1) {
+        if (pl.acc == 1) return launch_fused<MODE, 1>(pl, s);
     }
+    return launch_fused<MODE, 0>(pl, s);
+}
+
+// One plane of the two-pass path: prefix planes (+ column prefix and summed-area table for the hybrid walk),
+// then the gather kernel.  PM: plane mode; FIN: descriptor mode finished in place, or -1 for raw sums.
+template <int PM, int FIN>
+static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t s) {
+    const DiscParams& p = pl.p;
     const int warps = kThreads / 32;
-    TOPO_LAUNCH(kernel_label("disc_prefix", MODE, 0), s,
-                disc_prefix_kernel<MODE><<<ceil_div(pl.prefix_rows, warps), kThreads, 0, s>>>(p, pl.prefix_rows));
+    TOPO_LAUNCH(kernel_label("disc_prefix", PM, 0), s,
+                disc_prefix_kernel<PM><<<ceil_div(pl.prefix_rows, warps), kThreads, 0, s>>>(p, pl.prefix_rows));
+    const int grid = p.tiles_x * p.tiles_y;
+    const size_t smem = pl.smem + span_extra_smem();
     if (pl.hybrid) {
         unsigned char* ws = reinterpret_cast<unsigned char*>(p.planes);
         uint32_t* tot_q = reinterpret_cast<uint32_t*>(ws + pl.off_totq);
         unsigned long long* tot_r = reinterpret_cast<unsigned long long*>(ws + pl.off_totr);
         dim3 cgrid(ceil_div(p.pitch / 4, 256), pl.nchunks);
-        TOPO_LAUNCH("disc_colsum", s, disc_colsum_kernel<MODE><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
+        TOPO_LAUNCH("disc_colsum", s, disc_colsum_kernel<PM><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
         TOPO_LAUNCH("disc_chunkscan", s,
-                    disc_chunkscan_kernel<<<ceil_div(p.pitch, 256), 256, 0, s>>>(tot_q, tot_r, pl.nchunks, p.pitch,
-                                                                                    ModeTraits<MODE>::NARR));
-        TOPO_LAUNCH("disc_colapply", s, disc_colapply_kernel<MODE><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
-        static const int carve = span_carveout<MODE, ACC, true>();
-        (void)carve;
-        TOPO_LAUNCH(kernel_label("disc_hybrid", MODE, ACC), s,
-                    disc_span_kernel<MODE, ACC, true><<<p.tiles_x * p.tiles_y, kThreads, pl.smem + span_extra_smem(), s>>>(p));
+                    disc_chunkscan_kernel<<<ceil_div(p.pitch, 256), 256, 0, s>>>(tot_q, tot_r, pl.nchunks, p.pitch, 1));
+        TOPO_LAUNCH("disc_colapply", s, disc_colapply_kernel<PM><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
+        if (acc32)
+            TOPO_LAUNCH(kernel_label("disc_hybrid", PM, 1), s, disc_span_kernel<true, true, FIN><<<grid, kThreads, smem, s>>>(p, plane));
+        else
+            TOPO_LAUNCH(kernel_label("disc_hybrid", PM, 0), s, disc_span_kernel<false, true, FIN><<<grid, kThreads, smem, s>>>(p, plane));
     } else {
-        static const int carve = span_carveout<MODE, ACC, false>();
-        (void)carve;
-        TOPO_LAUNCH(kernel_label("disc_span", MODE, ACC), s,
-                    disc_span_kernel<MODE, ACC, false><<<p.tiles_x * p.tiles_y, kThreads, pl.smem + span_extra_smem(), s>>>(p));
+        if (acc32)
+            TOPO_LAUNCH(kernel_label("disc_span", PM, 1), s, disc_span_kernel<true, false, FIN><<<grid, kThreads, smem, s>>>(p, plane));
+        else
+            TOPO_LAUNCH(kernel_label("disc_span", PM, 0), s, disc_span_kernel<false, false, FIN><<<grid, kThreads, smem, s>>>(p, plane));
     }
     return 0;
 }
 
-template <int MODE>
-static int launch_disc_acc(const DiscPlan& pl, cudaStream_t s) {
-    constexpr int FULL = (1 << ModeTraits<MODE>::NARR) - 1;
-    if (pl.acc == FULL) return launch_disc<MODE, FULL>(pl, s);
-    if constexpr (FULL != 1) {
-        if (pl.acc == 1) return launch_disc<MODE, 1>(pl, s);
+// tsum_op: 0 = no sharing, 1 = compute the T plane and keep its raw sums in p.tsum, 2 = reuse p.tsum
+static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s) {
+    const bool a0 = pl.acc & 1, a1 = (pl.acc >> 1) & 1, a2 = (pl.acc >> 2) & 1;
+    const bool reuse = tsum_op == 2;
+    int rc = 0;
+    switch (pl.mode) {
+        case TPI_Q: return launch_plane<TPI_Q, TPI_Q>(pl, 0, a0, s);
+        case TPI_I:
+            if (!reuse) return launch_plane<PL_T, TPI_I>(pl, 0, a0, s);
+            TOPO_LAUNCH("disc_finish<TPI_I>", s, disc_finish_kernel<TPI_I><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
+            return 0;
+        case TPI_X:
+            if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s))) return rc;
+            if ((rc = launch_plane<PL_F, -1>(pl, 1, a1, s))) return rc;
+            TOPO_LAUNCH("disc_finish<TPI_X>", s, disc_finish_kernel<TPI_X><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
+            return 0;
+        case STD_I:
+            if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s))) return rc;
+            if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s))) return rc;
+            TOPO_LAUNCH("disc_finish<STD_I>", s, disc_finish_kernel<STD_I><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
+            return 0;
+        default:
+            if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s))) return rc;
+            if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s))) return rc;
+            if ((rc = launch_plane<PL_F, -1>(pl, 2, a2, s))) return rc;
+            TOPO_LAUNCH("disc_finish<STD_F>", s, disc_finish_kernel<STD_F><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
+            return 0;
     }
-    return launch_disc<MODE, 0>(pl, s);
 }
 
 static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,
-                    int what, int all_integer, double zmin, double zmax, void* ws, size_t ws_bytes, void* stream) {
+                    int what, int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op, void* ws,
+                    size_t ws_bytes, void* stream) {
     TOPO_CHECK(dem && out, "null pointer");
     if (validate_view(v)) return -1;
     TOPO_CHECK(ld_in >= v->nx && ld_out >= v->nx, "row pitch smaller than nx");
@@ -1036,24 +1147,35 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
     if (plan_disc(v, size, what, all_integer, zmin, zmax, pl)) return -1;
     if (check_band(v, pl.p.halo)) return -1;
     pl.p.dem = dem, pl.p.out = out, pl.p.ld_in = ld_in, pl.p.ld_out = ld_out;
+    cudaStream_t s = (cudaStream_t)stream;
     if (!pl.fused) {
         TOPO_CHECK(ws != nullptr && ws_bytes >= pl.ws_bytes, "workspace too small: need %zu bytes, got %zu",
                    pl.ws_bytes, ws_bytes);
         TOPO_CHECK((reinterpret_cast<uintptr_t>(ws) & 31) == 0, "workspace must be 32-byte aligned");
         TOPO_CHECK((long long)pl.p.tiles_x * pl.p.tiles_y < 2147483647ll, "too many tiles");
+        TOPO_CHECK((long long)pl.p.plane_stride + pl.p.pitch < 2147483647ll && (long long)pl.p.cplane_stride + pl.p.pitch < 2147483647ll,
+                   "band too large for 32-bit plane offsets: split the DEM in row bands");
         pl.p.planes = (uint32_t*)ws;
         if (pl.hybrid) {
             pl.p.cplanes = reinterpret_cast<uint32_t*>((unsigned char*)ws + pl.off_cp);
             pl.p.sat = reinterpret_cast<unsigned long long*>((unsigned char*)ws + pl.off_sat);
         }
+        pl.p.partial = reinterpret_cast<unsigned long long*>((unsigned char*)ws + pl.off_partial);
+        pl.p.dbg_skip = getenv("TOPO_DBG_SKIP") ? atoi(getenv("TOPO_DBG_SKIP")) : 0;
+        if (tsum_op != 0) {
+            TOPO_CHECK(tsum != nullptr, "tsum_op %d needs a T-plane sum buffer", tsum_op);
+            TOPO_CHECK(pl.mode != TPI_Q, "this size/DEM does not use the T plane (see topo_disc_shares_tsum)");
+            pl.p.tsum = tsum;
+        }
+        return launch_two_pass(pl, tsum_op, s);
     }
-    cudaStream_t s = (cudaStream_t)stream;
+    TOPO_CHECK(tsum_op == 0, "T-plane sums are only shared on the two-pass path (see topo_disc_shares_tsum)");
     switch (pl.mode) {
-        case TPI_Q: return launch_disc_acc<TPI_Q>(pl, s);
-        case TPI_I: return launch_disc_acc<TPI_I>(pl, s);
-        case TPI_X: return launch_disc_acc<TPI_X>(pl, s);
-        case STD_I: return launch_disc_acc<STD_I>(pl, s);
-        default: return launch_disc_acc<STD_F>(pl, s);
+        case TPI_Q: return launch_fused_acc<TPI_Q>(pl, s);
+        case TPI_I: return launch_fused_acc<TPI_I>(pl, s);
+        case TPI_X: return launch_fused_acc<TPI_X>(pl, s);
+        case STD_I: return launch_fused_acc<STD_I>(pl, s);
+        default: return launch_fused_acc<STD_F>(pl, s);
     }
 }
 
@@ -1078,14 +1200,27 @@ size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what) {
     return worst;
 }
 
+int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer) {
+    // tpi and std of the same size both run two-pass on the integer planes => std can reuse tpi's T-plane sums
+    if (!v || !all_integer || size < 2 || size > kMaxSize) return 0;
+    DiscPlan a, b;
+    memset(&a, 0, sizeof(a));
+    memset(&b, 0, sizeof(b));
+    plan_geometry(v, size, narr_of(TPI_I), max_rb(TPI_I), a);
+    plan_geometry(v, size, narr_of(STD_I), max_rb(STD_I), b);
+    return (!a.fused && !b.fused) ? 1 : 0;
+}
+
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,
-                 int all_integer, double zmin, double zmax, void* ws, size_t ws_bytes, void* stream) {
-    return run_disc(dem, ld_in, out, ld_out, v, size, 0, all_integer, zmin, zmax, ws, ws_bytes, stream);
+                 int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op, void* ws,
+                 size_t ws_bytes, void* stream) {
+    return run_disc(dem, ld_in, out, ld_out, v, size, 0, all_integer, zmin, zmax, tsum, tsum_op, ws, ws_bytes, stream);
 }
 
 int topo_std_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,
-                 int all_integer, double zmin, double zmax, void* ws, size_t ws_bytes, void* stream) {
-    return run_disc(dem, ld_in, out, ld_out, v, size, 1, all_integer, zmin, zmax, ws, ws_bytes, stream);
+                 int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op, void* ws,
+                 size_t ws_bytes, void* stream) {
+    return run_disc(dem, ld_in, out, ld_out, v, size, 1, all_integer, zmin, zmax, tsum, tsum_op, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

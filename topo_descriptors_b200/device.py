@@ -187,41 +187,53 @@ def _nan_result(v, like, n=1):
     return outs
 
 
-def tpi(dem, size, out_gy0=None, out_rows=None, out=None):
+def _tsum_plan(dem, v, size, st, share):
+    """T-plane sum sharing between tpi(size) and std(size) of the same integer-valued DEM band:
+    returns (tensor or None, op) with op 0 = off, 1 = compute + keep, 2 = reuse."""
+    torch = _torch()
+    if not share or st["nonint"] != 0:
+        return None, 0
+    L = _lib.load()
+    if not L.topo_disc_shares_tsum(ctypes.byref(v), int(size), 1):
+        return None, 0
+    key = (int(size), v.out_gy0, v.out_rows)
+    cached = getattr(dem, "_tsum", None)
+    if cached is not None and cached[0] == key:
+        dem._tsum = None  # consumed: a tpi+std pair is the use case, free the 8 B/px right after
+        return cached[1], 2
+    t = torch.empty((v.out_rows, dem.nx), dtype=torch.int64, device=dem.tensor.device)
+    dem._tsum = (key, t)
+    return t, 1
+
+
+def _disc(name, what, dem, size, out_gy0, out_rows, out, share):
+    torch = require_cuda()
+    v = dem.view(out_gy0, out_rows)
+    st = dem.stats
+    if out is None:
+        out = _new(v.out_rows, dem.nx, dem.tensor)
+    if st["nonfinite"] > 0:
+        fill(out, float("nan"))
+        return out
+    L = _lib.load()
+    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), what)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
+    tsum, op = _tsum_plan(dem, v, size, st, share)
+    _lib.call(name, _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
+              1 if st["nonint"] == 0 else 0, st["min"], st["max"], _ptr(tsum), op, _ptr(ws), ws_bytes, _stream())
+    return out
+
+
+def tpi(dem, size, out_gy0=None, out_rows=None, out=None, share=True):
     """Device TPI of global rows [out_gy0, out_gy0+out_rows); all-NaN if the DEM has non-finite values
-    (the reference's FFT convolution spreads them over the whole output)."""
-    torch = require_cuda()
-    v = dem.view(out_gy0, out_rows)
-    st = dem.stats
-    if out is None:
-        out = _new(v.out_rows, dem.nx, dem.tensor)
-    if st["nonfinite"] > 0:
-        fill(out, float("nan"))
-        return out
-    L = _lib.load()
-    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), 0)
-    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
-    _lib.call("topo_tpi_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
-              1 if st["nonint"] == 0 else 0, st["min"], st["max"], _ptr(ws), ws_bytes, _stream())
-    return out
+    (the reference's FFT convolution spreads them over the whole output).  ``share``: on integer-valued
+    DEMs keep / reuse the disc sums that tpi(size) and std(size) have in common (one gather pass less per pair)."""
+    return _disc("topo_tpi_f32", 0, dem, size, out_gy0, out_rows, out, share)
 
 
-def std(dem, size, out_gy0=None, out_rows=None, out=None):
+def std(dem, size, out_gy0=None, out_rows=None, out=None, share=True):
     """Device STD (float32; the host shim up-casts to float64 like the reference)."""
-    torch = require_cuda()
-    v = dem.view(out_gy0, out_rows)
-    st = dem.stats
-    if out is None:
-        out = _new(v.out_rows, dem.nx, dem.tensor)
-    if st["nonfinite"] > 0:
-        fill(out, float("nan"))
-        return out
-    L = _lib.load()
-    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), 1)
-    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
-    _lib.call("topo_std_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
-              1 if st["nonint"] == 0 else 0, st["min"], st["max"], _ptr(ws), ws_bytes, _stream())
-    return out
+    return _disc("topo_std_f32", 1, dem, size, out_gy0, out_rows, out, share)
 
 
 def _res_to_device(res, device):
