@@ -98,10 +98,12 @@ int topo_std_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, co
  * float32 round in between, reflect borders (d c b a | a b c d | d c b a) in global coordinates.
  * w_y / w_x: DEVICE arrays of lw+1 float64 half-kernels (w[0] = centre tap) computed by the host
  * exactly as scipy's _gaussian_kernel1d does; a null pointer skips that axis (sigma <= 1e-15).
- * `ws` holds the axis-0 result. */
+ * nan_safe != 0: the input may hold non-finite values; the kernels then predicate every tap so that NaN
+ * spreads exactly +-lw like scipy (needed because the register-blocked walk also visits zero-weight taps).
+ * `ws` holds the axis-0 result (+ two transposed planes when the axis-1 radius exceeds 64). */
 size_t topo_gauss_workspace_bytes(const topo_view* v, int lw_y, int lw_x);
 int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
-                   const double* w_y, int lw_y, const double* w_x, int lw_x, void* ws,
+                   const double* w_y, int lw_y, const double* w_x, int lw_x, int nan_safe, void* ws,
                    size_t ws_bytes, void* stream);
 
 /* ---- gradient / slope / aspect (topo.py:597-644, 688-712) -------------------------------------

@@ -208,6 +208,21 @@ def test_gaussian_c1(c1, sigma):
     _ulp_close(topo.dem(z, sigma), O.gaussian_filter_restated(z, sigma))
 
 
+def test_gaussian_nan_spreads_exactly_like_scipy():
+    z = fractal_dem(150, 170, seed=31)
+    z[40, 50] = np.nan
+    z[149, 0] = np.nan
+    z[70:72, 100] = np.inf
+    for sigma in (0.6, 1.75, 4.25, (2.0, 0.0), 20.0):
+        want = O.gaussian_filter_restated(z, sigma)
+        got = topo.dem(z, sigma)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), sigma
+        assert np.array_equal(np.isinf(got), np.isinf(want)), sigma
+        ok = np.isfinite(want)
+        if ok.any():  # sigma 20: the radius-80 window already covers every pixel
+            _ulp_close(got[ok], want[ok])
+
+
 def test_sobel_bit_exact(golden):
     dx, dy = topo.sobel(golden["in__z"])
     assert np.array_equal(dx, golden["sobel__dx"]) and np.array_equal(dy, golden["sobel__dy"])

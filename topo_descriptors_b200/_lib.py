@@ -49,7 +49,7 @@ PROTOTYPES = {
     "topo_std_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_int, c_int, c_double, c_double,
                              c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "topo_gauss_workspace_bytes": (c_size_t, [_VP, c_int, c_int]),
-    "topo_gauss_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_void_p, c_int, c_void_p, c_int,
+    "topo_gauss_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_void_p, c_int, c_void_p, c_int, c_int,
                                c_void_p, c_size_t, c_void_p]),
     "topo_grad_from_smooth_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int64, _VP, c_void_p, c_int, c_void_p, c_int, c_void_p]),

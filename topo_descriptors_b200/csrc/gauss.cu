@@ -51,9 +51,13 @@ __device__ __forceinline__ void stage_weights(const GaussParams& p, double* wful
 // global top or bottom edge pay for the reflect index arithmetic.
 constexpr int kA0Cols = 64;
 
+// NANSAFE: the DEM holds non-finite values; taps outside an output's own window (zero weight) must not touch
+// it (0 * NaN = NaN would spread NaN further than scipy's +-lw).
+template <bool NANSAFE>
 __global__ void __launch_bounds__(256, 2) gauss_axis0_kernel(const GaussParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* wfull = reinterpret_cast<double*>(smem_raw);
+    __shared__ long long rowoff[8][kK];  // per warp: element offset of the input row of each step of a group
     stage_weights(p, wfull, threadIdx.x + threadIdx.y * 32, 256);
     __syncthreads();
 
@@ -70,42 +74,29 @@ __global__ void __launch_bounds__(256, 2) gauss_axis0_kernel(const GaussParams p
 
     const int in_end = p.in_gy0 + p.in_rows;
     const int nsteps = gauss_steps(lw);
-    const int first = gy0 - lw, last = first + nsteps - 1;
-    const int lo_ok = p.in_gy0 > 0 ? p.in_gy0 : 0, hi_ok = in_end < p.gny ? in_end : p.gny;
+    const int first = gy0 - lw;
     const double* wp = wfull;
-    if (first >= lo_ok && last < hi_ok) {
-        const float* ptr = p.in + (int64_t)(first - p.in_gy0) * p.ld_in;
-        for (int n0 = 0; n0 < nsteps; n0 += kK, wp += kK) {
-#pragma unroll
-            for (int s = 0; s < kK; ++s) {
-#pragma unroll
-                for (int k = kK - 1; k > 0; --k) wr[k] = wr[k - 1];
-                wr[0] = wp[s];
-                const double da = (double)__ldg(ptr + xa), db = (double)__ldg(ptr + xb);
-                ptr += p.ld_in;
-#pragma unroll
-                for (int k = 0; k < kK; ++k) {
-                    acc0[k] = fma(wr[k], da, acc0[k]);
-                    acc1[k] = fma(wr[k], db, acc1[k]);
-                }
-            }
+    long long* ro = rowoff[threadIdx.y];
+    for (int n0 = 0; n0 < nsteps; n0 += kK, wp += kK) {
+        // lanes 0..K-1 resolve the input rows of this group (reflect at the global edges; rows outside the
+        // band can only carry zero weight or feed outputs that are not stored: clamp them into the band)
+        __syncwarp();
+        if (threadIdx.x < kK) {
+            int g = reflect_index(first + n0 + (int)threadIdx.x, p.gny);
+            g = g < p.in_gy0 ? p.in_gy0 : (g >= in_end ? in_end - 1 : g);
+            ro[threadIdx.x] = (long long)(g - p.in_gy0) * p.ld_in;
         }
-    } else {
-        for (int n0 = 0; n0 < nsteps; n0 += kK, wp += kK) {
+        __syncwarp();
 #pragma unroll
-            for (int s = 0; s < kK; ++s) {
+        for (int s = 0; s < kK; ++s) {
 #pragma unroll
-                for (int k = kK - 1; k > 0; --k) wr[k] = wr[k - 1];
-                wr[0] = wp[s];
-                const int g = reflect_index(first + n0 + s, p.gny);
-                float va = 0.f, vb = 0.f;
-                if (g >= p.in_gy0 && g < in_end) {
-                    const float* row = p.in + (int64_t)(g - p.in_gy0) * p.ld_in;
-                    va = __ldg(row + xa), vb = __ldg(row + xb);
-                }
-                const double da = (double)va, db = (double)vb;
+            for (int k = kK - 1; k > 0; --k) wr[k] = wr[k - 1];
+            wr[0] = wp[s];
+            const float* row = p.in + ro[s];
+            const double da = (double)__ldg(row + xa), db = (double)__ldg(row + xb);
 #pragma unroll
-                for (int k = 0; k < kK; ++k) {
+            for (int k = 0; k < kK; ++k) {
+                if (!NANSAFE || (unsigned)(n0 + s - k) <= (unsigned)(2 * lw)) {
                     acc0[k] = fma(wr[k], da, acc0[k]);
                     acc1[k] = fma(wr[k], db, acc1[k]);
                 }
@@ -144,6 +135,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 // block 256 = 8 warps.  Tile: 32 rows (lanes) x 128 output columns; warp w owns columns [w*K, w*K+K).
 constexpr int kA1Cols = 8 * kK;
 
+template <bool NANSAFE>
 __global__ void __launch_bounds__(256) gauss_axis1_kernel(const GaussParams p, int pitch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* wfull = reinterpret_cast<double*>(smem_raw);
@@ -185,7 +177,8 @@ __global__ void __launch_bounds__(256) gauss_axis1_kernel(const GaussParams p, i
                 wr[0] = wp[s];
                 const double dv = (double)tp[s];
 #pragma unroll
-                for (int k = 0; k < kK; ++k) acc[k] = fma(wr[k], dv, acc[k]);
+                for (int k = 0; k < kK; ++k)
+                    if (!NANSAFE || (unsigned)(n0 + s - k) <= (unsigned)(2 * lw)) acc[k] = fma(wr[k], dv, acc[k]);
             }
         }
 #pragma unroll
@@ -329,7 +322,7 @@ size_t topo_gauss_workspace_bytes(const topo_view* v, int lw_y, int lw_x) {
 }
 
 int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
-                   const double* w_y, int lw_y, const double* w_x, int lw_x, void* ws, size_t ws_bytes,
+                   const double* w_y, int lw_y, const double* w_x, int lw_x, int nan_safe, void* ws, size_t ws_bytes,
                    void* stream) {
     TOPO_CHECK(in && out, "null pointer");
     if (validate_view(v)) return -1;
@@ -357,7 +350,10 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
         dim3 grid(ceil_div(v->nx, kA0Cols), ceil_div(v->out_rows, 8 * kK));
         const size_t smem = (size_t)gauss_steps(lw_y) * sizeof(double);
         TOPO_CHECK(smem <= 48 * 1024, "gaussian radius %d too large", lw_y);
-        TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<<<grid, dim3(32, 8), smem, s>>>(p));
+        if (nan_safe)
+            TOPO_LAUNCH("gauss_axis0<nansafe>", s, gauss_axis0_kernel<true><<<grid, dim3(32, 8), smem, s>>>(p));
+        else
+            TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<false><<<grid, dim3(32, 8), smem, s>>>(p));
         cur = dst, cur_ld = dst_ld, cur_gy0 = v->out_gy0, cur_rows = v->out_rows;
     } else {
         TOPO_CHECK(v->in_gy0 <= v->out_gy0 && v->in_gy0 + v->in_rows >= v->out_gy0 + v->out_rows,
@@ -379,7 +375,10 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
         dim3 grid(ceil_div(v->out_rows, kA0Cols), ceil_div(v->nx, 8 * kK));
         const size_t smem = (size_t)gauss_steps(lw_x) * sizeof(double);
         TOPO_CHECK(smem <= 48 * 1024, "gaussian radius %d too large", lw_x);
-        TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<<<grid, dim3(32, 8), smem, s>>>(p));
+        if (nan_safe)
+            TOPO_LAUNCH("gauss_axis0<nansafe>", s, gauss_axis0_kernel<true><<<grid, dim3(32, 8), smem, s>>>(p));
+        else
+            TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<false><<<grid, dim3(32, 8), smem, s>>>(p));
         dim3 tg2(ceil_div(v->out_rows, 32), ceil_div(v->nx, 32));
         TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg2, dim3(32, 8), 0, s>>>(t2, tpitch, out, ld_out, v->nx, v->out_rows));
     } else if (do_x) {
@@ -391,12 +390,16 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
         int dev = 0;
         TOPO_CUDA(cudaGetDevice(&dev));
         if (dev < 64 && !attr_set[dev]) {
-            TOPO_CUDA(cudaFuncSetAttribute(gauss_axis1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            TOPO_CUDA(cudaFuncSetAttribute(gauss_axis1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            TOPO_CUDA(cudaFuncSetAttribute(gauss_axis1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_set[dev] = true;
         }
         GaussParams p{cur, out, cur_ld, ld_out, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_x, lw_x};
         dim3 grid(ceil_div(v->nx, kA1Cols), ceil_div(v->out_rows, 32));
-        TOPO_LAUNCH("gauss_axis1", s, gauss_axis1_kernel<<<grid, 256, smem, s>>>(p, pitch));
+        if (nan_safe)
+            TOPO_LAUNCH("gauss_axis1<nansafe>", s, gauss_axis1_kernel<true><<<grid, 256, smem, s>>>(p, pitch));
+        else
+            TOPO_LAUNCH("gauss_axis1", s, gauss_axis1_kernel<false><<<grid, 256, smem, s>>>(p, pitch));
     } else if (!do_y) {
         TOPO_CUDA(cudaMemcpy2DAsync(out, ld_out * sizeof(float),
                                     in + (int64_t)(v->out_gy0 - v->in_gy0) * ld_in, ld_in * sizeof(float),

@@ -175,8 +175,11 @@ def gauss(dem, sigma_y, sigma_x, out_gy0=None, out_rows=None, out=None):
     L = _lib.load()
     ws_bytes = L.topo_gauss_workspace_bytes(ctypes.byref(v), lwy, lwx)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
+    # NaN-exact taps only when the DEM is known (or not yet known) to hold non-finite values
+    st = dem._stats if dem._stats is not None else (dem.stats if dem.is_whole else None)
+    nan_safe = 1 if (st is None or st["nonfinite"] > 0) else 0
     _lib.call("topo_gauss_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), _ptr(wy), lwy,
-              _ptr(wx), lwx, _ptr(ws), ws_bytes, _stream())
+              _ptr(wx), lwx, nan_safe, _ptr(ws), ws_bytes, _stream())
     return out
 
 
