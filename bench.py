@@ -214,8 +214,8 @@ def run_gpu(args, rank, world, local_rank):
 
     host = torch.from_numpy(make_dem_rows(ny, nx, ctx.r0, ctx.r1)).pin_memory()
     core = host.to(device, non_blocking=True)
-    res_x = (torch.full((nx,), RES_M, dtype=torch.float64, device=device), 0)
-    res_y = (torch.full((ny,), -RES_M, dtype=torch.float64, device=device), 0)
+    res_x = (dev._Res(np.full(nx, RES_M), device), 0)
+    res_y = (dev._Res(np.full(ny, -RES_M), device), 0)
     torch.cuda.synchronize()
 
     def barrier():

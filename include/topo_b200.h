@@ -115,13 +115,16 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
 int topo_grad_from_smooth_f32(const float* gx, const float* gy, int64_t ld_in, float* dx, float* dy,
                               float* slope, float* aspect, int64_t ld_out, const topo_view* v,
                               const double* res_x, int res_x_2d, const double* res_y, int res_y_2d,
-                              void* stream);
+                              const float* res_xf, const float* res_yf, void* stream);
 /* Sobel branch, sigma <= 1 (topo.py:628-629, 658-685): ndimage.convolve with K/8 and K.T/8,
- * reflect borders, float64 accumulation; same normalisation / slope / aspect epilogue fused. */
+ * reflect borders, float64 accumulation; same normalisation / slope / aspect epilogue fused.
+ * res_xf / res_yf (both entry points, optional): float32 copies of the resolution arrays, to be passed
+ * only when every value is exactly representable in float32 -- the float32 division then rounds
+ * identically to numpy's float64 one and the kernels can take their 128-bit vector path. */
 int topo_sobel_gradient_f32(const float* dem, int64_t ld_in, float* dx, float* dy, float* slope,
                             float* aspect, int64_t ld_out, const topo_view* v, const double* res_x,
-                            int res_x_2d, const double* res_y, int res_y_2d, int normalize,
-                            void* stream);
+                            int res_x_2d, const double* res_y, int res_y_2d, const float* res_xf,
+                            const float* res_yf, int normalize, void* stream);
 
 /* ---- Sx (topo.py:775-858, 928-953) --------------------------------------------------------------
  * n_az azimuth sectors in one launch.  offsets: (dy, dx) int pairs of the de-duplicated ray

@@ -52,9 +52,9 @@ PROTOTYPES = {
     "topo_gauss_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_void_p, c_int, c_void_p, c_int, c_int,
                                c_void_p, c_size_t, c_void_p]),
     "topo_grad_from_smooth_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                          c_int64, _VP, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+                                          c_int64, _VP, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "topo_sobel_gradient_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, _VP,
-                                        c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+                                        c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "topo_sx_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, _VP, c_void_p, c_void_p, c_void_p,
                             c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "topo_zscore_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_float, c_void_p]),

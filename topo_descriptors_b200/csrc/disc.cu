@@ -97,6 +97,7 @@ struct DiscParams {
     // epilogue constants
     double inv_scale, inv_fscale, n, inv_nm1;
     long long n_ll;
+    double nc0_scaled, n_tmin;  // N*c0 (TPI_Q: times 2^-S folded in) and N*tmin as doubles, for the 32-bit epilogue
     double inv_n_nm1;  // 1 / (N * (N - 1))
     int exact64;       // N*B - a^2 fits in 64-bit integers
     int excl;          // TPI: offset (excl, excl) of the excluded "mid point" (0 odd size, -1 even size)
@@ -447,6 +448,202 @@ __global__ void __launch_bounds__(kThreads) disc_fused_kernel(const DiscParams p
         unsigned long long acc[RB][2][NARR];
         span_walk<MODE, ACC, false>(p, P, plane_stride, p.pitch, tab, ty + p.halo, tp + p.haloL, acc);
         store_batch<MODE, kTW / 2>(p, acc, y0 + ty, y0 + ty, y_end, x);
+    }
+}
+
+// ---- tiny discs (odd sizes 5..13): direct sliding sums in registers ---------------------------------------
+// No prefix sums.  A thread owns one column of a 128 x 128 tile strip and walks down the rows: for every input
+// row it builds the symmetric row sums R_w = sum_{|j| <= w} q[Y][x+j] for w = 0..M by widening (2M loads,
+// 2M adds) and adds R_{w_r} to the 2M+1 output rows y = Y - r that are open, held in rotating registers
+// (all indices are compile-time after unrolling by 2M+1).  ~4M+2 integer ops and 2M+1 conflict-free LDS per
+// pixel and plane; squares of STD are derived on the fly (one IMAD) instead of being loaded.
+constexpr int kTinyTile = 128;  // tile edge; 8 warps = 4 column groups x 2 row strips of 64 rows
+constexpr int kTinyStrip = 64;
+
+template <int M>
+struct TinyWidths {
+    // w[r] = half-width of kernel row at vertical offset |r|, circular_kernel(2M+1): floor(sqrt(M^2 - r^2))
+    __host__ __device__ static constexpr int w(int r) {
+        int rem = M * M - r * r, v = 0;
+        while ((v + 1) * (v + 1) <= rem) ++v;
+        return v;
+    }
+};
+
+template <int MODE>
+struct TinyTraits;
+template <>
+struct TinyTraits<TPI_I> { static constexpr int LP = 1; static constexpr bool SQ = false; };
+template <>
+struct TinyTraits<TPI_Q> { static constexpr int LP = 1; static constexpr bool SQ = false; };
+template <>
+struct TinyTraits<TPI_X> { static constexpr int LP = 2; static constexpr bool SQ = false; };
+template <>
+struct TinyTraits<STD_I> { static constexpr int LP = 1; static constexpr bool SQ = true; };
+template <>
+struct TinyTraits<STD_F> { static constexpr int LP = 2; static constexpr bool SQ = true; };
+
+// the planes a tiny kernel LOADS (the square plane of STD is derived from plane 0)
+template <int MODE>
+__device__ __forceinline__ void convert_tiny(const DiscParams& p, float z, uint32_t (&v)[TinyTraits<MODE>::LP]) {
+    if constexpr (MODE == TPI_Q) {
+        v[0] = (uint32_t)(__float2int_rn(z * p.scale) - p.c0i);
+    } else {
+        const int t = __float2int_rz(z);
+        v[0] = (uint32_t)(t - p.tmin);
+        if constexpr (TinyTraits<MODE>::LP == 2) v[1] = (uint32_t)__float2int_rn(((z - (float)t) + 1.0f) * p.fscale);
+    }
+}
+
+template <int MODE, int M>
+__global__ void __launch_bounds__(256) disc_tiny_kernel(const DiscParams p) {
+    constexpr int D = 2 * M + 1;
+    constexpr int LP = TinyTraits<MODE>::LP;
+    constexpr bool SQ = TinyTraits<MODE>::SQ;
+    constexpr int NS = LP + (SQ ? 1 : 0);          // sums kept per output pixel
+    constexpr int NARR = ModeTraits<MODE>::NARR;   // == NS, in the order (T, Q, F) / (T, F) / (q)
+    static_assert(NS == NARR, "plane bookkeeping");
+    constexpr int TC = kTinyTile + 2 * M;          // tile columns
+    constexpr int PITCH = TC + 1;
+    constexpr int STEPS = ((kTinyStrip + 2 * M + D - 1) / D) * D;  // input rows walked per strip (multiple of D)
+    constexpr int TR = kTinyStrip + STEPS;         // tile rows: strip 1 starts 64 rows below strip 0
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem_raw);  // [LP][TR][PITCH]
+
+    const int x0 = blockIdx.x * kTinyTile;
+    const int y0 = p.out_gy0 + blockIdx.y * kTinyTile;  // global row of the tile's first output row
+    const int in_end = p.in_gy0 + p.in_rows;
+
+    // ---- stage the converted tile: rows y0-M .. y0-M+TR-1, columns x0-M .. x0-M+TC-1, zero padding outside.
+    // Two rows x ceil(TC/32) loads are issued before the first use (the loop bounds are compile-time).
+    {
+        constexpr int CI = (TC + 31) / 32;
+        const int lane_ = threadIdx.x & 31;
+        for (int r = (threadIdx.x >> 5) * 2; r < TR; r += 16) {
+            float z[2][CI];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int gy = y0 - M + r + rr;
+                const bool row_ok = r + rr < TR && gy >= 0 && gy < p.gny && gy >= p.in_gy0 && gy < in_end;
+                const float* src = p.dem + (int64_t)(gy - p.in_gy0) * p.ld_in;
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) {
+                    const int c = ci * 32 + lane_, gx = x0 - M + c;
+                    z[rr][ci] = (row_ok && c < TC && gx >= 0 && gx < p.nx) ? __ldg(src + gx) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (r + rr >= TR) break;
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) {
+                    const int c = ci * 32 + lane_;
+                    if (c < TC) {
+                        uint32_t v[LP];
+                        convert_tiny<MODE>(p, z[rr][ci], v);
+#pragma unroll
+                        for (int a = 0; a < LP; ++a) tile[(a * TR + r + rr) * PITCH + c] = v[a];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cg = warp & 3, strip = warp >> 2;
+    const int tx = cg * 32 + lane;                 // tile column of this thread's pixel column
+    const int x = x0 + tx;
+    const int ys = y0 + strip * kTinyStrip;        // global row of the strip's first output row
+    const int y_end = p.out_gy0 + p.out_rows;
+    if (ys >= y_end) return;
+    const uint32_t* col = tile + (strip * kTinyStrip) * PITCH + tx + M;  // input row Y=-M of the strip, centre column
+    const int dq = p.cmid - p.tmin;                // (t - cmid) = (t - tmin) - dq
+
+    uint32_t acc[D][NS];
+    float zc[D];  // TPI: the pixel's own elevation, fetched when its slot opens (2M steps before it is needed)
+#pragma unroll
+    for (int s = 0; s < D; ++s) {
+        zc[s] = 0.f;
+#pragma unroll
+        for (int a = 0; a < NS; ++a) acc[s][a] = 0u;
+    }
+    constexpr bool IS_TPI = (MODE == TPI_I || MODE == TPI_Q || MODE == TPI_X);
+    const int xz = x < p.nx ? x : p.nx - 1;
+
+#pragma unroll 1
+    for (int j = 0; j < STEPS / D; ++j) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) {
+            // input row Y = D*j + s - M (relative to the strip); tile row D*j + s
+            const uint32_t* row = col + (D * j + s) * PITCH;
+            uint32_t R[M + 1][NS];
+            // widening: R[w] = R[w-1] + q[-w] + q[+w]
+#pragma unroll
+            for (int w = 0; w <= M; ++w) {
+#pragma unroll
+                for (int a = 0; a < LP; ++a) {
+                    const uint32_t* pl = row + a * TR * PITCH;
+                    if (w == 0) {
+                        const uint32_t c0 = pl[0];
+                        R[0][a == 0 ? 0 : NS - 1] = c0;
+                        if (SQ && a == 0) {
+                            const int d0 = (int)c0 - dq;
+                            R[0][1] = (uint32_t)(d0 * d0);
+                        }
+                    } else {
+                        const uint32_t l = pl[-w], r = pl[w];
+                        R[w][a == 0 ? 0 : NS - 1] = R[w - 1][a == 0 ? 0 : NS - 1] + l + r;
+                        if (SQ && a == 0) {
+                            const int dl = (int)l - dq, dr = (int)r - dq;
+                            R[w][1] = R[w - 1][1] + (uint32_t)(dl * dl) + (uint32_t)(dr * dr);
+                        }
+                    }
+                }
+            }
+            // output rows y = Y - r, r = -M..M, live in slot (s - M - r) mod D; r = -M opens the slot, r = +M closes it
+#pragma unroll
+            for (int r = -M; r <= M; ++r) {
+                constexpr int BIG = 4 * D;
+                const int slot = (s - M - r + BIG) % D;
+                const int w = TinyWidths<M>::w(r < 0 ? -r : r);
+#pragma unroll
+                for (int a = 0; a < NS; ++a) {
+                    if (r == -M)
+                        acc[slot][a] = R[w][a];
+                    else
+                        acc[slot][a] += R[w][a];
+                }
+                if (IS_TPI && r == -M) {
+                    const int gyo = ys + D * j + s;  // output row whose slot opens now: Y + M = D*j + s (strip-relative)
+                    zc[slot] = (gyo < y_end && D * j + s < kTinyStrip) ? __ldg(p.dem + (int64_t)(gyo - p.in_gy0) * p.ld_in + xz) : 0.f;
+                }
+                if (r == M) {
+                    const int yo = D * j + s - 2 * M;  // output row (strip-relative) that just received its last row
+                    const int gy = ys + yo;
+                    if (yo >= 0 && yo < kTinyStrip && gy < y_end && x < p.nx) {
+                        float res;
+                        if constexpr (MODE == TPI_I || MODE == TPI_Q || MODE == TPI_X) {
+                            // odd size: the excluded mid point is the pixel itself
+                            const double z = (double)zc[slot];
+                            double sz = (double)acc[slot][0];
+                            if constexpr (MODE == TPI_Q)
+                                sz = fma(sz, p.inv_scale, p.nc0_scaled);
+                            else
+                                sz += p.n_tmin;
+                            if constexpr (MODE == TPI_X) sz += (double)acc[slot][1] * p.inv_fscale - p.n;
+                            res = (float)(fma(z, p.n - 1.0, z - sz) * p.inv_nm1);
+                        } else {
+                            unsigned long long a64[NARR];
+#pragma unroll
+                            for (int a = 0; a < NS; ++a) a64[a] = acc[slot][a];
+                            res = finish<MODE>(p, a64, gy, x);
+                        }
+                        p.out[(int64_t)(gy - p.out_gy0) * p.ld_out + x] = res;
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -822,7 +1019,7 @@ __global__ void __launch_bounds__(256) disc_finish_kernel(const DiscParams p) {
 struct DiscPlan {
     DiscParams p;
     int mode, acc;
-    bool fused, hybrid;
+    bool fused, hybrid, tiny;
     size_t smem;
     int prefix_rows;  // two-pass
     int nchunks;      // hybrid: column-scan chunks
@@ -998,9 +1195,14 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
         if (n * vmax[a] < kU32) acc |= 1 << a;
     pl.mode = mode;
     if (plan_geometry(v, size, narr_of(mode), max_rb(mode), pl)) return -1;
+    pl.tiny = false;
     if (pl.fused) {
         // instantiated accumulator layouts of the fused kernels: none, plane 0 only, all planes
         const int full = (1 << narr_of(mode)) - 1;
+        // tiny odd discs whose sums fit 32 bits: direct register sliding sums instead of prefix sums
+        // (one loaded plane only: with two the 128 x 128 tile leaves a single CTA per SM and the prefix kernel wins)
+        pl.tiny = (size & 1) && size >= 5 && size <= 13 && acc == full && (mode == TPI_I || mode == TPI_Q || mode == STD_I) &&
+                  !getenv("TOPO_NO_TINY");
         if (acc != full) acc &= 1;
     }
     pl.acc = acc;
@@ -1009,6 +1211,8 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
     p.inv_n_nm1 = 1.0 / (n * (n - 1.0));
     p.exact64 = (n * (floor(trange / 2.0) + 1.0)) < 3.0e9;
     p.inv_nm1 = 1.0 / (n - 1.0);
+    p.nc0_scaled = n * (double)p.c0i * p.inv_scale;
+    p.n_tmin = n * (double)p.tmin;
     return 0;
 }
 
@@ -1068,6 +1272,35 @@ static int launch_fused_acc(const DiscPlan& pl, cudaStream_t s) {
         if (pl.acc == 1) return launch_fused<MODE, 1>(pl, s);
     }
     return launch_fused<MODE, 0>(pl, s);
+}
+
+template <int MODE, int M>
+static int launch_tiny(const DiscPlan& pl, cudaStream_t s) {
+    const DiscParams& p = pl.p;
+    constexpr int D = 2 * M + 1;
+    constexpr int STEPS = ((kTinyStrip + 2 * M + D - 1) / D) * D;
+    constexpr size_t smem = (size_t)TinyTraits<MODE>::LP * (kTinyStrip + STEPS) * (kTinyTile + 2 * M + 1) * 4;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    TOPO_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        TOPO_CUDA(cudaFuncSetAttribute(disc_tiny_kernel<MODE, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        attr_set[dev] = true;
+    }
+    dim3 grid(ceil_div(p.nx, kTinyTile), ceil_div(p.out_rows, kTinyTile));
+    TOPO_LAUNCH(kernel_label("disc_tiny", MODE, 2 * M + 1), s, disc_tiny_kernel<MODE, M><<<grid, 256, smem, s>>>(p));
+    return 0;
+}
+
+template <int MODE>
+static int launch_tiny_m(const DiscPlan& pl, cudaStream_t s) {
+    switch (pl.p.mid) {
+        case 2: return launch_tiny<MODE, 2>(pl, s);
+        case 3: return launch_tiny<MODE, 3>(pl, s);
+        case 4: return launch_tiny<MODE, 4>(pl, s);
+        case 5: return launch_tiny<MODE, 5>(pl, s);
+        default: return launch_tiny<MODE, 6>(pl, s);
+    }
 }
 
 // One plane of the two-pass path: prefix planes (+ column prefix and summed-area table for the hybrid walk),
@@ -1170,6 +1403,15 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
         return launch_two_pass(pl, tsum_op, s);
     }
     TOPO_CHECK(tsum_op == 0, "T-plane sums are only shared on the two-pass path (see topo_disc_shares_tsum)");
+    if (pl.tiny) {
+        switch (pl.mode) {
+            case TPI_Q: return launch_tiny_m<TPI_Q>(pl, s);
+            case TPI_I: return launch_tiny_m<TPI_I>(pl, s);
+            case TPI_X: return launch_tiny_m<TPI_X>(pl, s);
+            case STD_I: return launch_tiny_m<STD_I>(pl, s);
+            default: return launch_tiny_m<STD_F>(pl, s);
+        }
+    }
     switch (pl.mode) {
         case TPI_Q: return launch_fused_acc<TPI_Q>(pl, s);
         case TPI_I: return launch_fused_acc<TPI_I>(pl, s);

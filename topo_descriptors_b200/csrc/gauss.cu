@@ -132,23 +132,30 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 }
 
 // ---- axis 1 (along x), radius <= kAxis1SmemMaxRadius ---------------------------------------------------
-// block 256 = 8 warps.  Tile: 32 rows (lanes) x 128 output columns; warp w owns columns [w*K, w*K+K).
-constexpr int kA1Cols = 8 * kK;
+// block 256 = 8 warps.  Tile: 32 rows (lanes) x 8*K output columns; warp w owns columns [w*K, w*K+K).
+// K = 8 for small radii (the walk visits K + 2*lw taps rounded up to K: less padding), 16 otherwise.
+template <int K>
+__host__ __device__ __forceinline__ int axis1_steps(int lw) { return ((K + 2 * lw + K - 1) / K) * K; }
 
-template <bool NANSAFE>
+template <int K, bool NANSAFE>
 __global__ void __launch_bounds__(256) gauss_axis1_kernel(const GaussParams p, int pitch) {
+    constexpr int COLS = 8 * K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* wfull = reinterpret_cast<double*>(smem_raw);
-    const int nsteps = gauss_steps(p.lw);
+    const int nsteps = axis1_steps<K>(p.lw);
     float* tile = reinterpret_cast<float*>(wfull + nsteps);  // [32][pitch]
-    float* otile = tile + (size_t)32 * pitch;                // [32][kA1Cols + 1]
+    float* otile = tile + (size_t)32 * pitch;                // [32][COLS + 1]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lw = p.lw;
-    stage_weights(p, wfull, threadIdx.x, 256);
+    for (int n = threadIdx.x; n < nsteps; n += 256) {
+        int a = n - lw;
+        a = a < 0 ? -a : a;
+        wfull[n] = (a <= lw) ? p.w[a] : 0.0;
+    }
 
-    const int x0 = blockIdx.x * kA1Cols;
+    const int x0 = blockIdx.x * COLS;
     const int r0 = blockIdx.y * 32;  // first row (relative to the output band) of this tile
-    const int span = kA1Cols + nsteps - kK;  // columns a thread group can touch: c0 + n, n < nsteps
+    const int span = COLS + nsteps - K;  // columns a thread group can touch: c0 + n, n < nsteps
     // stage: warp per row, lanes along x, reflect at the global left/right edges
     for (int r = warp; r < 32; r += 8) {
         const int row = r0 + r;
@@ -163,35 +170,58 @@ __global__ void __launch_bounds__(256) gauss_axis1_kernel(const GaussParams p, i
     __syncthreads();
 
     {
-        const int c0 = warp * kK;  // first output column (tile-relative) of this thread
+        const int c0 = warp * K;  // first output column (tile-relative) of this thread
         const float* tp = tile + (size_t)lane * pitch + c0;  // input x0 + c0 + (n - lw) sits at tile column c0 + n
         const double* wp = wfull;
-        double acc[kK], wr[kK];
+        double acc[K], wr[K];
 #pragma unroll
-        for (int k = 0; k < kK; ++k) acc[k] = 0.0, wr[k] = 0.0;
-        for (int n0 = 0; n0 < nsteps; n0 += kK, wp += kK, tp += kK) {
+        for (int k = 0; k < K; ++k) acc[k] = 0.0, wr[k] = 0.0;
+        for (int n0 = 0; n0 < nsteps; n0 += K, wp += K, tp += K) {
 #pragma unroll
-            for (int s = 0; s < kK; ++s) {
+            for (int s = 0; s < K; ++s) {
 #pragma unroll
-                for (int k = kK - 1; k > 0; --k) wr[k] = wr[k - 1];
+                for (int k = K - 1; k > 0; --k) wr[k] = wr[k - 1];
                 wr[0] = wp[s];
                 const double dv = (double)tp[s];
 #pragma unroll
-                for (int k = 0; k < kK; ++k)
+                for (int k = 0; k < K; ++k)
                     if (!NANSAFE || (unsigned)(n0 + s - k) <= (unsigned)(2 * lw)) acc[k] = fma(wr[k], dv, acc[k]);
             }
         }
 #pragma unroll
-        for (int k = 0; k < kK; ++k) otile[lane * (kA1Cols + 1) + c0 + k] = (float)acc[k];
+        for (int k = 0; k < K; ++k) otile[lane * (COLS + 1) + c0 + k] = (float)acc[k];
     }
     __syncthreads();
     for (int r = warp; r < 32; r += 8) {
         const int row = r0 + r;
         if (row >= p.out_rows) break;
         float* dst = p.out + (int64_t)row * p.ld_out;
-        for (int c = lane; c < kA1Cols; c += 32)
-            if (x0 + c < p.nx) dst[x0 + c] = otile[r * (kA1Cols + 1) + c];
+        for (int c = lane; c < COLS; c += 32)
+            if (x0 + c < p.nx) dst[x0 + c] = otile[r * (COLS + 1) + c];
     }
+}
+
+template <int K>
+static int launch_axis1(const GaussParams& p, int nan_safe, cudaStream_t s) {
+    constexpr int COLS = 8 * K;
+    const int nsteps = axis1_steps<K>(p.lw);
+    int pitch = COLS + nsteps - K;
+    pitch |= 1;  // odd pitch: lanes (rows) hit distinct banks
+    const size_t smem = (size_t)nsteps * sizeof(double) + ((size_t)32 * pitch + (size_t)32 * (COLS + 1)) * sizeof(float);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    TOPO_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !attr_set[dev]) {
+        TOPO_CUDA(cudaFuncSetAttribute(gauss_axis1_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TOPO_CUDA(cudaFuncSetAttribute(gauss_axis1_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev] = true;
+    }
+    dim3 grid(ceil_div(p.nx, COLS), ceil_div(p.out_rows, 32));
+    if (nan_safe)
+        TOPO_LAUNCH("gauss_axis1<nansafe>", s, gauss_axis1_kernel<K, true><<<grid, 256, smem, s>>>(p, pitch));
+    else
+        TOPO_LAUNCH("gauss_axis1", s, gauss_axis1_kernel<K, false><<<grid, 256, smem, s>>>(p, pitch));
+    return 0;
 }
 
 // ---- derivative / slope / aspect epilogue ------------------------------------------------------------
@@ -203,6 +233,8 @@ struct GradParams {
     int nx, gny, in_gy0, in_rows, out_gy0, out_rows;
     const double* res_x;
     const double* res_y;
+    const float* res_xf;  // optional float32 copies (exactly equal to the float64 arrays)
+    const float* res_yf;
     int res_x_2d, res_y_2d, normalize;
 };
 
@@ -213,6 +245,19 @@ __device__ __forceinline__ float div_by_res(float v, double r) {
     const float rf = (float)r;
     if ((double)rf == r) return __fdiv_rn(v, rf);
     return (float)((double)v / r);
+}
+
+// slope / aspect of one pixel in the reference's float32 operation order (topo.py:639-642)
+__device__ __forceinline__ void slope_aspect(float dx, float dy, float& slope, float& aspect) {
+    // np.arctan(np.sqrt(dx**2 + dy**2)) * (180 / np.pi)
+    const float h2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    slope = __fmul_rn(atanf(sqrtf(h2)), 57.29577951308232f);
+    // (180 + np.degrees(np.arctan2(dx, dy))) % 360; np.degrees on float32 multiplies by 180.0f / NPY_PIf =
+    // 57.2957763671875f (one ulp below float32(180/pi) used for the slope)
+    const float deg = __fmul_rn(atan2f(dx, dy), 57.2957763671875f);
+    float a = __fadd_rn(180.0f, deg);
+    if (a >= 360.0f) a -= 360.0f;  // a is in [0, 360]: Python's % 360 only maps 360 -> 0; NaN stays NaN
+    aspect = a;
 }
 
 __device__ __forceinline__ void finish_gradient(const GradParams& p, float dx, float dy, int gy, int x) {
@@ -227,59 +272,132 @@ __device__ __forceinline__ void finish_gradient(const GradParams& p, float dx, f
     p.dx[o] = dx;
     p.dy[o] = dy;
     if (p.slope) {
-        // np.arctan(np.sqrt(dx**2 + dy**2)) * (180 / np.pi), every step in float32
-        const float h2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-        p.slope[o] = __fmul_rn(atanf(sqrtf(h2)), 57.29577951308232f);
-    }
-    if (p.aspect) {
-        // (180 + np.degrees(np.arctan2(dx, dy))) % 360 in float32, Python modulo
-        // np.degrees on float32 multiplies by 180.0f / NPY_PIf = 57.2957763671875f (one ulp below
-        // float32(180/pi) used for the slope above)
-        const float deg = __fmul_rn(atan2f(dx, dy), 57.2957763671875f);
-        // a is in [0, 360] (|deg| <= 180), so Python's % 360 only maps 360 -> 0; NaN stays NaN
-        float a = __fadd_rn(180.0f, deg);
-        if (a >= 360.0f) a -= 360.0f;
-        p.aspect[o] = a;
+        float sl, as;
+        slope_aspect(dx, dy, sl, as);
+        p.slope[o] = sl;
+        p.aspect[o] = as;
     }
 }
 
-__global__ void __launch_bounds__(256) grad_from_smooth_kernel(const GradParams p) {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int gy = p.out_gy0 + blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= p.nx || gy >= p.out_gy0 + p.out_rows) return;
-    const float* rx = p.gx + (int64_t)(gy - p.in_gy0) * p.ld_in;
+// generic per-pixel path (image borders, unaligned rasters, float64-only resolutions)
+template <bool SOBEL>
+__device__ __forceinline__ void gradient_pixel(const GradParams& p, int gy, int x) {
     float dx, dy;
-    if (x == 0)
-        dx = __fsub_rn(__ldg(rx + 1), __ldg(rx));
-    else if (x == p.nx - 1)
-        dx = __fsub_rn(__ldg(rx + x), __ldg(rx + x - 1));
-    else
-        dx = __fdiv_rn(__fsub_rn(__ldg(rx + x + 1), __ldg(rx + x - 1)), 2.0f);
-    const float* cy = p.gy + (int64_t)(gy - p.in_gy0) * p.ld_in + x;
-    if (gy == 0)
-        dy = __fsub_rn(__ldg(cy + p.ld_in), __ldg(cy));
-    else if (gy == p.gny - 1)
-        dy = __fsub_rn(__ldg(cy), __ldg(cy - p.ld_in));
-    else
-        dy = __fdiv_rn(__fsub_rn(__ldg(cy + p.ld_in), __ldg(cy - p.ld_in)), 2.0f);
+    if (SOBEL) {
+        const int xm = reflect_index(x - 1, p.nx), xp = reflect_index(x + 1, p.nx);
+        const float* r0 = p.gx + (int64_t)(reflect_index(gy - 1, p.gny) - p.in_gy0) * p.ld_in;
+        const float* r1 = p.gx + (int64_t)(gy - p.in_gy0) * p.ld_in;
+        const float* r2 = p.gx + (int64_t)(reflect_index(gy + 1, p.gny) - p.in_gy0) * p.ld_in;
+        const double a = __ldg(r0 + xm), b = __ldg(r0 + x), c = __ldg(r0 + xp);
+        const double d = __ldg(r1 + xm), f = __ldg(r1 + xp);
+        const double g = __ldg(r2 + xm), h = __ldg(r2 + x), i = __ldg(r2 + xp);
+        // exact in float64 (<= 6 terms of 24-bit values), one rounding to float32 like ndimage
+        dx = (float)(((c + 2.0 * f + i) - (a + 2.0 * d + g)) * 0.125);
+        dy = (float)(((g + 2.0 * h + i) - (a + 2.0 * b + c)) * 0.125);
+    } else {
+        const float* rx = p.gx + (int64_t)(gy - p.in_gy0) * p.ld_in;
+        if (x == 0)
+            dx = __fsub_rn(__ldg(rx + 1), __ldg(rx));
+        else if (x == p.nx - 1)
+            dx = __fsub_rn(__ldg(rx + x), __ldg(rx + x - 1));
+        else
+            dx = __fmul_rn(__fsub_rn(__ldg(rx + x + 1), __ldg(rx + x - 1)), 0.5f);
+        const float* cy = p.gy + (int64_t)(gy - p.in_gy0) * p.ld_in + x;
+        if (gy == 0)
+            dy = __fsub_rn(__ldg(cy + p.ld_in), __ldg(cy));
+        else if (gy == p.gny - 1)
+            dy = __fsub_rn(__ldg(cy), __ldg(cy - p.ld_in));
+        else
+            dy = __fmul_rn(__fsub_rn(__ldg(cy + p.ld_in), __ldg(cy - p.ld_in)), 0.5f);
+    }
     finish_gradient(p, dx, dy, gy, x);
 }
 
-__global__ void __launch_bounds__(256) sobel_gradient_kernel(const GradParams p) {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+// block 256 = 64 pixel quads x 4 rows: tile 256 x 4.  Interior tiles of aligned rasters take the vector path
+// (128-bit loads and streaming stores, 4 pixels per thread); everything else goes pixel by pixel.
+template <bool SOBEL>
+__global__ void __launch_bounds__(256) gradient_kernel(const GradParams p, int vec_ok) {
+    const int tq = threadIdx.x & 63;
+    const int x0 = blockIdx.x * 256;
     const int gy = p.out_gy0 + blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= p.nx || gy >= p.out_gy0 + p.out_rows) return;
-    const int xm = reflect_index(x - 1, p.nx), xp = reflect_index(x + 1, p.nx);
-    const float* r0 = p.gx + (int64_t)(reflect_index(gy - 1, p.gny) - p.in_gy0) * p.ld_in;
-    const float* r1 = p.gx + (int64_t)(gy - p.in_gy0) * p.ld_in;
-    const float* r2 = p.gx + (int64_t)(reflect_index(gy + 1, p.gny) - p.in_gy0) * p.ld_in;
-    const double a = __ldg(r0 + xm), b = __ldg(r0 + x), c = __ldg(r0 + xp);
-    const double d = __ldg(r1 + xm), f = __ldg(r1 + xp);
-    const double g = __ldg(r2 + xm), h = __ldg(r2 + x), i = __ldg(r2 + xp);
-    // exact in float64 (<= 6 terms of 24-bit values), one rounding to float32 like ndimage
-    const float dx = (float)(((c + 2.0 * f + i) - (a + 2.0 * d + g)) * 0.125);
-    const float dy = (float)(((g + 2.0 * h + i) - (a + 2.0 * b + c)) * 0.125);
-    finish_gradient(p, dx, dy, gy, x);
+    const int ty0 = p.out_gy0 + blockIdx.y * 4;
+    const bool interior = vec_ok && x0 >= 4 && x0 + 256 + 4 <= p.nx && ty0 >= 1 && ty0 + 4 + 1 <= p.gny &&
+                          ty0 + 4 <= p.out_gy0 + p.out_rows && ty0 - 1 >= p.in_gy0 && ty0 + 5 <= p.in_gy0 + p.in_rows;
+    if (!interior) {
+        if (gy >= p.out_gy0 + p.out_rows) return;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + 4 * tq + j;
+            if (x < p.nx) gradient_pixel<SOBEL>(p, gy, x);
+        }
+        return;
+    }
+    const int x = x0 + 4 * tq;
+    float dxv[4], dyv[4];
+    if (SOBEL) {
+        const float* r0 = p.gx + (int64_t)(gy - 1 - p.in_gy0) * p.ld_in + x;
+        const float* r1 = r0 + p.ld_in;
+        const float* r2 = r1 + p.ld_in;
+        const float4 m0 = ldg4(r0), m1 = ldg4(r1), m2 = ldg4(r2);
+        const float v0[6] = {__ldg(r0 - 1), m0.x, m0.y, m0.z, m0.w, __ldg(r0 + 4)};
+        const float v1[6] = {__ldg(r1 - 1), m1.x, m1.y, m1.z, m1.w, __ldg(r1 + 4)};
+        const float v2[6] = {__ldg(r2 - 1), m2.x, m2.y, m2.z, m2.w, __ldg(r2 + 4)};
+        double cs[6], rd[6];  // column sums (1,2,1) and row differences, exact in float64
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const double a = (double)v0[t], b = (double)v1[t], c = (double)v2[t];
+            cs[t] = (a + c) + 2.0 * b;
+            rd[t] = c - a;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dxv[j] = (float)((cs[j + 2] - cs[j]) * 0.125);
+            dyv[j] = (float)(((rd[j] + rd[j + 2]) + 2.0 * rd[j + 1]) * 0.125);
+        }
+    } else {
+        const float* rx = p.gx + (int64_t)(gy - p.in_gy0) * p.ld_in + x;
+        const float4 m = ldg4(rx);
+        const float v[6] = {__ldg(rx - 1), m.x, m.y, m.z, m.w, __ldg(rx + 4)};
+        const float* cy = p.gy + (int64_t)(gy - p.in_gy0) * p.ld_in + x;
+        const float4 up = ldg4(cy - p.ld_in), dn = ldg4(cy + p.ld_in);
+        const float u[4] = {up.x, up.y, up.z, up.w}, d[4] = {dn.x, dn.y, dn.z, dn.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dxv[j] = __fmul_rn(__fsub_rn(v[j + 2], v[j]), 0.5f);
+            dyv[j] = __fmul_rn(__fsub_rn(d[j], u[j]), 0.5f);
+        }
+    }
+    float sl[4], as[4];
+    if (p.normalize) {
+        float rxv[4], ryv[4];
+        if (p.res_x_2d) {
+            const float4 t = ldg4(p.res_xf + (int64_t)gy * p.nx + x);
+            rxv[0] = t.x, rxv[1] = t.y, rxv[2] = t.z, rxv[3] = t.w;
+        } else {
+            const float4 t = ldg4(p.res_xf + x);
+            rxv[0] = t.x, rxv[1] = t.y, rxv[2] = t.z, rxv[3] = t.w;
+        }
+        if (p.res_y_2d) {
+            const float4 t = ldg4(p.res_yf + (int64_t)gy * p.nx + x);
+            ryv[0] = t.x, ryv[1] = t.y, ryv[2] = t.z, ryv[3] = t.w;
+        } else {
+            ryv[0] = ryv[1] = ryv[2] = ryv[3] = __ldg(p.res_yf + gy);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dxv[j] = __fdiv_rn(dxv[j], rxv[j]);
+            dyv[j] = __fdiv_rn(dyv[j], ryv[j]);
+        }
+    }
+    const int64_t o = (int64_t)(gy - p.out_gy0) * p.ld_out + x;
+    st4_streaming(p.dx + o, make_float4(dxv[0], dxv[1], dxv[2], dxv[3]));
+    st4_streaming(p.dy + o, make_float4(dyv[0], dyv[1], dyv[2], dyv[3]));
+    if (p.slope) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) slope_aspect(dxv[j], dyv[j], sl[j], as[j]);
+        st4_streaming(p.slope + o, make_float4(sl[0], sl[1], sl[2], sl[3]));
+        st4_streaming(p.aspect + o, make_float4(as[0], as[1], as[2], as[3]));
+    }
 }
 
 static int check_rows_reflect(const topo_view* v, int lo_off, int hi_off, const char* what) {
@@ -382,24 +500,9 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
         dim3 tg2(ceil_div(v->out_rows, 32), ceil_div(v->nx, 32));
         TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg2, dim3(32, 8), 0, s>>>(t2, tpitch, out, ld_out, v->nx, v->out_rows));
     } else if (do_x) {
-        const int nsteps = gauss_steps(lw_x);
-        int pitch = kA1Cols + nsteps - kK;
-        pitch |= 1;  // odd pitch: lanes (rows) hit distinct banks
-        const size_t smem = (size_t)nsteps * sizeof(double) + ((size_t)32 * pitch + (size_t)32 * (kA1Cols + 1)) * sizeof(float);
-        static bool attr_set[64] = {false};
-        int dev = 0;
-        TOPO_CUDA(cudaGetDevice(&dev));
-        if (dev < 64 && !attr_set[dev]) {
-            TOPO_CUDA(cudaFuncSetAttribute(gauss_axis1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            TOPO_CUDA(cudaFuncSetAttribute(gauss_axis1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_set[dev] = true;
-        }
         GaussParams p{cur, out, cur_ld, ld_out, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_x, lw_x};
-        dim3 grid(ceil_div(v->nx, kA1Cols), ceil_div(v->out_rows, 32));
-        if (nan_safe)
-            TOPO_LAUNCH("gauss_axis1<nansafe>", s, gauss_axis1_kernel<true><<<grid, 256, smem, s>>>(p, pitch));
-        else
-            TOPO_LAUNCH("gauss_axis1", s, gauss_axis1_kernel<false><<<grid, 256, smem, s>>>(p, pitch));
+        const int rc = lw_x <= 12 ? launch_axis1<8>(p, nan_safe, s) : launch_axis1<16>(p, nan_safe, s);
+        if (rc) return rc;
     } else if (!do_y) {
         TOPO_CUDA(cudaMemcpy2DAsync(out, ld_out * sizeof(float),
                                     in + (int64_t)(v->out_gy0 - v->in_gy0) * ld_in, ld_in * sizeof(float),
@@ -410,35 +513,44 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
 
 static int run_grad(bool sobel, const float* gx, const float* gy, int64_t ld_in, float* dx, float* dy, float* slope,
                     float* aspect, int64_t ld_out, const topo_view* v, const double* res_x, int res_x_2d,
-                    const double* res_y, int res_y_2d, int normalize, void* stream) {
+                    const double* res_y, int res_y_2d, const float* res_xf, const float* res_yf, int normalize,
+                    void* stream) {
     TOPO_CHECK(gx && gy && dx && dy, "null pointer");
     if (validate_view(v)) return -1;
     TOPO_CHECK(v->nx >= 2 && v->gny >= 2, "gradient needs at least 2 x 2 pixels");
     TOPO_CHECK(!normalize || (res_x && res_y), "missing resolution arrays");
+    TOPO_CHECK((slope == nullptr) == (aspect == nullptr), "slope and aspect go together");
     if (v->out_rows == 0) return 0;
     if (check_rows_reflect(v, -1, 1, sobel ? "sobel" : "gradient")) return -1;
     GradParams p{gx, gy, dx, dy, slope, aspect, ld_in, ld_out, v->nx, v->gny, v->in_gy0, v->in_rows,
-                 v->out_gy0, v->out_rows, res_x, res_y, res_x_2d, res_y_2d, normalize};
-    dim3 grid(ceil_div(v->nx, 64), ceil_div(v->out_rows, 4));
+                 v->out_gy0, v->out_rows, res_x, res_y, res_xf, res_yf, res_x_2d, res_y_2d, normalize};
+    // vector path: 16-byte aligned rows everywhere and float32 resolutions at hand
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    int vec_ok = (ld_in % 4 == 0) && (ld_out % 4 == 0) && (v->nx % 4 == 0) && al16(gx) && al16(gy) && al16(dx) && al16(dy) &&
+                 (!slope || (al16(slope) && al16(aspect)));
+    if (normalize) vec_ok = vec_ok && res_xf && res_yf && al16(res_xf) && al16(res_yf);
+    dim3 grid(ceil_div(v->nx, 256), ceil_div(v->out_rows, 4));
     cudaStream_t s = (cudaStream_t)stream;
     if (sobel)
-        TOPO_LAUNCH("sobel_gradient", s, sobel_gradient_kernel<<<grid, 256, 0, s>>>(p));
+        TOPO_LAUNCH("sobel_gradient", s, gradient_kernel<true><<<grid, 256, 0, s>>>(p, vec_ok));
     else
-        TOPO_LAUNCH("grad_from_smooth", s, grad_from_smooth_kernel<<<grid, 256, 0, s>>>(p));
+        TOPO_LAUNCH("grad_from_smooth", s, gradient_kernel<false><<<grid, 256, 0, s>>>(p, vec_ok));
     return 0;
 }
 
 int topo_grad_from_smooth_f32(const float* gx, const float* gy, int64_t ld_in, float* dx, float* dy, float* slope,
                               float* aspect, int64_t ld_out, const topo_view* v, const double* res_x, int res_x_2d,
-                              const double* res_y, int res_y_2d, void* stream) {
-    return run_grad(false, gx, gy, ld_in, dx, dy, slope, aspect, ld_out, v, res_x, res_x_2d, res_y, res_y_2d, 1, stream);
+                              const double* res_y, int res_y_2d, const float* res_xf, const float* res_yf, void* stream) {
+    return run_grad(false, gx, gy, ld_in, dx, dy, slope, aspect, ld_out, v, res_x, res_x_2d, res_y, res_y_2d, res_xf,
+                    res_yf, 1, stream);
 }
 
 int topo_sobel_gradient_f32(const float* dem, int64_t ld_in, float* dx, float* dy, float* slope, float* aspect,
                             int64_t ld_out, const topo_view* v, const double* res_x, int res_x_2d,
-                            const double* res_y, int res_y_2d, int normalize, void* stream) {
-    return run_grad(true, dem, dem, ld_in, dx, dy, slope, aspect, ld_out, v, res_x, res_x_2d, res_y, res_y_2d,
-                    normalize, stream);
+                            const double* res_y, int res_y_2d, const float* res_xf, const float* res_yf, int normalize,
+                            void* stream) {
+    return run_grad(true, dem, dem, ld_in, dx, dy, slope, aspect, ld_out, v, res_x, res_x_2d, res_y, res_y_2d, res_xf,
+                    res_yf, normalize, stream);
 }
 
 }  // extern "C"

@@ -239,19 +239,45 @@ def std(dem, size, out_gy0=None, out_rows=None, out=None, share=True):
     return _disc("topo_std_f32", 1, dem, size, out_gy0, out_rows, out, share)
 
 
+class _Res:
+    """Grid resolution array on the device: float64 (reference semantics) plus, when every value is exactly
+    representable in float32, a float32 copy that lets the gradient kernels use their vector path."""
+
+    def __init__(self, res, device):
+        r = np.ascontiguousarray(np.asarray(res, dtype=np.float64))
+        self.f64 = _torch().from_numpy(r).to(device)
+        self.is_2d = int(r.ndim == 2)
+        r32 = r.astype(np.float32)
+        self.f32 = _torch().from_numpy(r32).to(device) if np.array_equal(r32.astype(np.float64), r) else None
+
+
 def _res_to_device(res, device):
-    r = np.ascontiguousarray(np.asarray(res, dtype=np.float64))
-    return _torch().from_numpy(r).to(device), int(r.ndim == 2)
+    """Back-compatible helper: (float64 device tensor, is_2d)."""
+    r = _Res(res, device)
+    return r.f64, r.is_2d
+
+
+def _as_res(x, is_2d=None):
+    if isinstance(x, _Res):
+        return x
+    r = _Res.__new__(_Res)
+    r.f64, r.is_2d = x, int(x.dim() == 2 if is_2d is None else is_2d)
+    f32 = x.to(_torch().float32)
+    r.f32 = f32 if bool((f32.to(_torch().float64) == x).all()) else None
+    return r
 
 
 def gradient_from_smooth(gx, gy, res_x_dev, res_x_2d, res_y_dev, res_y_2d, out_gy0=None, out_rows=None):
-    """[dx, dy, slope, aspect] from smoothed bands gx (d/dx) and gy (d/dy) (same band geometry)."""
+    """[dx, dy, slope, aspect] from smoothed bands gx (d/dx) and gy (d/dy) (same band geometry).
+    res_*_dev: `_Res` objects (preferred) or float64 device tensors."""
     require_cuda()
     v = gx.view(out_gy0, out_rows)
+    rx, ry = _as_res(res_x_dev, res_x_2d), _as_res(res_y_dev, res_y_2d)
+    f32 = rx.f32 is not None and ry.f32 is not None
     outs = [_new(v.out_rows, gx.nx, gx.tensor) for _ in range(4)]
     _lib.call("topo_grad_from_smooth_f32", _ptr(gx.tensor), _ptr(gy.tensor), gx.ld, _ptr(outs[0]), _ptr(outs[1]),
-              _ptr(outs[2]), _ptr(outs[3]), int(outs[0].stride(0)), ctypes.byref(v), _ptr(res_x_dev), res_x_2d,
-              _ptr(res_y_dev), res_y_2d, _stream())
+              _ptr(outs[2]), _ptr(outs[3]), int(outs[0].stride(0)), ctypes.byref(v), _ptr(rx.f64), rx.is_2d,
+              _ptr(ry.f64), ry.is_2d, _ptr(rx.f32 if f32 else None), _ptr(ry.f32 if f32 else None), _stream())
     return outs
 
 
@@ -262,10 +288,17 @@ def sobel_gradient(dem, res_x_dev=None, res_x_2d=0, res_y_dev=None, res_y_2d=0, 
     v = dem.view(out_gy0, out_rows)
     n_out = 4 if normalize else 2
     outs = [_new(v.out_rows, dem.nx, dem.tensor) for _ in range(n_out)]
+    null = ctypes.c_void_p(0)
+    if normalize:
+        rx, ry = _as_res(res_x_dev, res_x_2d), _as_res(res_y_dev, res_y_2d)
+        f32 = rx.f32 is not None and ry.f32 is not None
+        res_args = (_ptr(rx.f64), rx.is_2d, _ptr(ry.f64), ry.is_2d, _ptr(rx.f32 if f32 else None),
+                    _ptr(ry.f32 if f32 else None))
+    else:
+        res_args = (null, 0, null, 0, null, null)
     _lib.call("topo_sobel_gradient_f32", _ptr(dem.tensor), dem.ld, _ptr(outs[0]), _ptr(outs[1]),
-              _ptr(outs[2]) if normalize else ctypes.c_void_p(0), _ptr(outs[3]) if normalize else ctypes.c_void_p(0),
-              int(outs[0].stride(0)), ctypes.byref(v), _ptr(res_x_dev), res_x_2d, _ptr(res_y_dev), res_y_2d,
-              1 if normalize else 0, _stream())
+              _ptr(outs[2]) if normalize else null, _ptr(outs[3]) if normalize else null,
+              int(outs[0].stride(0)), ctypes.byref(v), *res_args, 1 if normalize else 0, _stream())
     return outs
 
 

@@ -322,8 +322,8 @@ def gradient(dem, sigma, res_meters, sig_ratio=1):
     m = _Marshal(dem)
     d = m.ddem
     device = d.tensor.device
-    rx, rx2d = dev._res_to_device(res_meters["x"], device)
-    ry, ry2d = dev._res_to_device(res_meters["y"], device)
+    rx, ry = dev._Res(res_meters["x"], device), dev._Res(res_meters["y"], device)
+    rx2d, ry2d = rx.is_2d, ry.is_2d
     if sigma <= 1:
         outs = dev.sobel_gradient(d, rx, rx2d, ry, ry2d, normalize=True)
     else:
