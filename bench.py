@@ -313,19 +313,41 @@ def run_gpu(args, rank, world, local_rank):
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
     dom_name, dom_v = dom
     avg_ms = dom_v["ms"] / dom_v["launches"]
-    alg_bytes = 8 * band_px  # every kernel on this path reads 4 B and writes 4 B per pixel
-    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+
+    def alg_bytes_px(name):
+        """Algorithmic HBM bytes per output pixel of one launch."""
+        if name.startswith(("grad_from_smooth", "sobel_gradient")):
+            return 20  # 4 B read + 4 outputs
+        if name.startswith("stats"):
+            return 4
+        return 8  # every other kernel on this path: 4 B in, 4 B out
+
+    achieved = alg_bytes_px(dom_name) * band_px / (avg_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
         "share_of_step": round(dom_v["ms"] / total_kernel_ms, 3),
-        "note": "dominant kernel by time is the large-radius span walk / Gaussian: shared-memory/L1 and FP64-issue bound, not HBM bound (DESIGN.md); per-kernel table in `kernels`",
+        "note": "the kernels that dominate config 4 are the wide-radius ones (float64 Gaussian taps, disc span gathers): "
+                "FP64-pipe / L1-wavefront bound by construction, so their HBM fraction is small; the HBM-bound kernels of "
+                "the path are listed in `memory_bound` (DESIGN.md section 4)",
     }
+    if dom_name.startswith("gauss_axis0"):
+        # float64 FMA roofline of the Gaussian: taps walked per pixel and launch (K + 2*lw rounded up to K = 16)
+        steps = [((16 + 2 * int(4.0 * sg + 0.5) + 15) // 16) * 16 for sg in sigmas]
+        n_launch = {True: 2, False: 1}
+        flops = sum(2.0 * band_px * st * n_launch[int(4.0 * sg + 0.5) > 64] for st, sg in zip(steps, sigmas))
+        roofline["fp64"] = {"achieved_tflops": round(flops / (dom_v["ms"] * 1e-3) / 1e12, 2),
+                            "peak_tflops": 29.7, "peak_source": "profiles/micro/pipes2.cu: 51 DFMA/clk/SM x 148 SM x 1.965 GHz"}
     kernels = {
         k: {"launches": v["launches"], "ms": round(v["ms"], 3), "avg_ms": round(v["ms"] / v["launches"], 4),
             "max_ms": round(v["max_ms"], 3),
-            "avg_GBps_alg": round(8 * band_px / (v["ms"] / v["launches"] * 1e-3) / 1e9, 1)}
+            "avg_GBps_alg": round(alg_bytes_px(k) * band_px / (v["ms"] / v["launches"] * 1e-3) / 1e9, 1)}
         for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+    }
+    memory_bound = {
+        k: {"GBps_alg": v["avg_GBps_alg"], "frac_of_hbm_peak": round(v["avg_GBps_alg"] / peak, 3)}
+        for k, v in kernels.items()
+        if k.startswith(("stats_partial", "grad_from_smooth", "sobel_gradient", "disc_tiny", "disc_prefix", "transpose"))
     }
 
     line = {
@@ -340,6 +362,7 @@ def run_gpu(args, rank, world, local_rank):
                 "path": "pinned host DEM -> HBM -> bands.sweep -> every output band back to pinned host memory (D2H on a second stream, overlapped)"},
         "gpu_launches": int(launches * args.steps),
         "roofline": roofline,
+        "memory_bound": memory_bound,
         "kernels": kernels,
     }
     if world == 1 and not args.no_cpu:

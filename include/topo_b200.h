@@ -129,12 +129,16 @@ int topo_sobel_gradient_f32(const float* dem, int64_t ld_in, float* dx, float* d
 /* ---- Sx (topo.py:775-858, 928-953) --------------------------------------------------------------
  * n_az azimuth sectors in one launch.  offsets: (dy, dx) int pairs of the de-duplicated ray
  * samples of all sectors, inv_dist: 1/distance per sample (float32), az_begin[n_az+1]: CSR ranges
- * (all DEVICE arrays).  dy_min/dy_max: extreme row offsets over all samples (band check).
+ * (all DEVICE arrays).  dy_min..dx_max: extreme offsets over all samples (band check, box size).
+ * When a 128 x 16 tile plus the sample extents fits a 256 x 256 TMA box (and 150 KB), the DEM tile is
+ * staged in shared memory by one cp.async.bulk.tensor per CTA and all azimuths of a CTA scan it from
+ * shared memory; otherwise the samples are gathered through L1.  The angle is atanf in float32.
  * out: [n_az] planes `az_stride` elements apart.  Pixels within `window` of any GLOBAL edge are 0;
  * NaN samples are skipped, a NaN centre or an empty sample list gives NaN (np.nanmax semantics). */
 int topo_sx_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int64_t az_stride,
                 const topo_view* v, const int* offsets, const float* inv_dist, const int* az_begin,
-                int n_az, int window, float height, int dy_min, int dy_max, void* stream);
+                int n_az, int window, float height, int dy_min, int dy_max, int dx_min, int dx_max,
+                void* stream);
 
 /* ---- valley / ridge (topo.py:389-453) ------------------------------------------------------------
  * z-score with the global mean/std (topo.py:429), then ALL angles in one launch with a running

@@ -302,15 +302,16 @@ def sobel_gradient(dem, res_x_dev=None, res_x_2d=0, res_y_dev=None, res_y_2d=0, 
     return outs
 
 
-def sx(dem, offsets_dev, inv_dist_dev, az_begin_dev, n_az, window, height, dy_min, dy_max, out_gy0=None,
-       out_rows=None):
-    """Sx for n_az azimuth sectors in one launch -> tensor (n_az, out_rows, nx)."""
+def sx(dem, offsets_dev, inv_dist_dev, az_begin_dev, n_az, window, height, extents, out_gy0=None, out_rows=None):
+    """Sx for n_az azimuth sectors in one launch -> tensor (n_az, out_rows, nx).
+    extents = (dy_min, dy_max, dx_min, dx_max) over all samples."""
     torch = require_cuda()
     v = dem.view(out_gy0, out_rows)
     out = torch.empty((n_az, v.out_rows, dem.nx), dtype=torch.float32, device=dem.tensor.device)
+    dy_min, dy_max, dx_min, dx_max = (int(e) for e in extents)
     _lib.call("topo_sx_f32", _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(1)), int(out.stride(0)),
-              ctypes.byref(v), _ptr(offsets_dev), _ptr(inv_dist_dev), _ptr(az_begin_dev), int(n_az), int(window),
-              float(height), int(dy_min), int(dy_max), _stream())
+              ctypes.byref(v), _ptr(offsets_dev), _ptr(inv_dist_dev), _ptr(az_begin_dev), int(n_az),
+              int(window), float(height), dy_min, dy_max, dx_min, dx_max, _stream())
     return out
 
 

@@ -389,7 +389,7 @@ def _sx_plan(dem_ds, azimuths_centre, radius, azimuth_arc, azimuth_steps, radius
     return offsets.reshape(-1, 2), inv, np.array(begin, dtype=np.int32), window
 
 
-def _sx_device(ddem, plan, height):
+def _sx_device(ddem, plan, height, out_gy0=None, out_rows=None):
     import torch
 
     offsets, inv, begin, window = plan
@@ -397,9 +397,12 @@ def _sx_device(ddem, plan, height):
     off_d = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int32)).to(device)
     inv_d = torch.from_numpy(np.ascontiguousarray(inv, dtype=np.float32)).to(device)
     beg_d = torch.from_numpy(begin).to(device)
-    dy_min = int(offsets[:, 0].min()) if len(offsets) else 0
-    dy_max = int(offsets[:, 0].max()) if len(offsets) else 0
-    return dev.sx(ddem, off_d, inv_d, beg_d, len(begin) - 1, window, height, dy_min, dy_max)
+    n_az = len(begin) - 1
+    if len(offsets):
+        extents = (offsets[:, 0].min(), offsets[:, 0].max(), offsets[:, 1].min(), offsets[:, 1].max())
+    else:
+        extents = (0, 0, 0, 0)
+    return dev.sx(ddem, off_d, inv_d, beg_d, n_az, window, height, extents, out_gy0, out_rows)
 
 
 @hlp.timer
