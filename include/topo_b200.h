@@ -148,14 +148,17 @@ int topo_sx_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int
  * a multiple of 4 and >= h + 3.  The kernels are already channel-mixed (the reference's 3-D
  * convolution sums neighbouring flat-list kernels, topo.py:431,443) and flipped, so the device
  * correlates:  out[y,x] = sum Kf[i,j] * d[y + i - h/2, x + j - w/2], zero outside the image.
- * bank_hw (DEVICE): 4 ints per angle: h, w, hp, 0.  hmax/wmax: maxima of h and w over the angles.
+ * bank_hw (DEVICE): 4 ints per angle: h, w, hp, c0.  hmax/wmax: maxima of h and w over the angles.
+ * bank_cols (DEVICE): for column j of angle a, at int index 2 * (c0 + j): (lo, n) -- the rows lo .. lo+n-1
+ * of that kernel column are walked, lo and n multiples of 4, lo + n <= hp, every weight outside
+ * [lo, lo + n - 4] exactly zero (the corners of a rotated kernel: ~37% of the bounding boxes).
  * dir receives the angle index (degrees, angles are 0..n_angles-1). */
 int topo_zscore_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int rows, int nx,
                     float mean, float std, void* stream);
 int topo_valley_ridge_f32(const float* dem_norm, int64_t ld_in, float* norm, float* dir, int64_t ld_out,
                           const topo_view* v, const float* bank, const int* bank_hw,
-                          const int64_t* bank_off, int n_angles, int n_ch, int hmax, int wmax,
-                          void* stream);
+                          const int64_t* bank_off, const int* bank_cols, int n_angles, int n_ch,
+                          int hmax, int wmax, void* stream);
 
 #ifdef __cplusplus
 }

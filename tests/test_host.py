@@ -113,9 +113,14 @@ def test_valley_bank(golden):
     bank = geo.build_valley_bank(7, "valley", [0, 0.15, 0.3])
     assert bank["n_angles"] == 180 and bank["n_ch"] == 3
     for a in (0, 33, 90, 179):
-        h, w, hp, _ = bank["hw"][a]
+        h, w, hp, c0 = bank["hw"][a]
         assert hp % 4 == 0 and hp >= h + 3 and bank["off"][a] % 4 == 0
         blk = bank["data"][bank["off"][a] : bank["off"][a] + w * hp * 4].reshape(w, hp, 4)
+        # the walked row range of every kernel column holds all its non-zero weights + 3 trailing zero rows
+        for j in range(w):
+            lo, n = bank["cols"][c0 + j]
+            assert lo % 4 == 0 and n % 4 == 0 and lo + n <= hp
+            assert not blk[j, :lo].any() and not blk[j, max(lo + n - 3, 0):].any()
         want = O.valley_ridge_channel_kernels(O.rotate_kernels(O.valley_kernels(7, [0, 0.15, 0.3]), np.float32(a)))
         got = np.transpose(blk[:, :h, :3], (2, 1, 0))[:, ::-1, ::-1]  # undo flip + layout
         assert np.allclose(got, want, atol=1e-5)

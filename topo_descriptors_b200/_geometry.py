@@ -130,7 +130,8 @@ def mix_channels(kernels_rot):
 def build_valley_bank(size, mode, flat_list, angles=None):
     """Pack the 180-angle bank for ``topo_valley_ridge_f32`` (layout in include/topo_b200.h):
     per angle a [w][hp][4] float32 block of the channel-mixed kernels, flipped in both axes so the
-    device correlates, rows h..hp-1 zero."""
+    device correlates, rows h..hp-1 zero; plus, per kernel column, the 4-aligned row range (lo, n) outside
+    which every weight is exactly zero (the corners of the rotated bounding box), so the device skips them."""
     if mode not in ("valley", "ridge"):
         raise ValueError(f"Unknown mode {mode!r}")
     flat_list = list(flat_list)
@@ -140,7 +141,7 @@ def build_valley_bank(size, mode, flat_list, angles=None):
     if angles is None:
         angles = np.arange(0, 180, dtype=np.float32)
     n_ch = base.shape[0]
-    blocks, hw, off = [], [], []
+    blocks, hw, off, cols = [], [], [], []
     pos = 0
     for ang in angles:
         mixed = mix_channels(rotate_kernels(base, ang))
@@ -150,11 +151,23 @@ def build_valley_bank(size, mode, flat_list, angles=None):
         blk = np.zeros((w, hp, 4), dtype=np.float32)
         blk[:, :h, :F] = np.transpose(flipped, (2, 1, 0))
         blocks.append(blk.ravel())
-        hw.append((h, w, hp, 0))
+        hw.append((h, w, hp, len(cols)))
+        nonzero = (blk != 0).any(axis=2)
+        for j in range(w):
+            rows = np.flatnonzero(nonzero[j])
+            if len(rows) == 0:
+                cols.append((0, 0))
+                continue
+            # the sliding window of 4 pixels needs weight rows first .. last + 3 (the tail rows are zero)
+            lo = int(rows[0]) & ~3
+            n = 4 * ((int(rows[-1]) + 4 - lo + 3) // 4)
+            assert lo + n <= hp
+            cols.append((lo, n))
         off.append(pos)
         pos += blk.size
     hw = np.array(hw, dtype=np.int32)
     return {
         "data": np.concatenate(blocks), "hw": hw, "off": np.array(off, dtype=np.int64),
+        "cols": np.array(cols, dtype=np.int32).reshape(-1, 2),
         "n_angles": len(off), "n_ch": n_ch, "hmax": int(hw[:, 0].max()), "wmax": int(hw[:, 1].max()),
     }

@@ -6,20 +6,21 @@
 // lives in registers for all 180 angles; norm is clipped at 0 on the way out.  Zero padding outside
 // the global image, scipy 'same' centring through the per-angle anchors.
 //
-// Register blocking: a thread owns 4 vertically adjacent pixels of one column (lanes = columns, so the
-// shared-memory DEM reads are conflict-free) and walks a kernel column top to bottom: each DEM sample
-// feeds 4 pixels x n_ch channels = up to 16 FMAs, with a rotating window of 4 weight vectors.  The DEM
-// tile + halo is staged once per CTA and reused by all angles; weights are warp-uniform 128-bit loads
-// served by L1/L2.
+// Register blocking: a thread owns 4 vertically adjacent pixels in each of 2 columns 32 apart (lanes = columns,
+// so the shared-memory DEM reads are conflict-free) and walks a kernel column top to bottom: each step loads one
+// weight vector (warp-uniform 128-bit load served by L1) and one DEM sample per column and issues
+// 2 x 4 x n_ch FMAs (24 for the usual 3 flats) with a rotating window of 4 weight vectors -- ~85% of the issue
+// slots are FFMA.  The DEM tile + halo is staged once per CTA and reused by all angles.
 #include <math.h>
 
 #include "common.cuh"
 
 namespace topo {
 
-constexpr int kVQ = 4;           // pixels per thread (vertical)
-constexpr int kVTileX = 32;      // block (32, 8): 32 columns x 8 thread rows x 4 pixels
-constexpr int kVTileY = 8 * kVQ; // 32 output rows per CTA
+constexpr int kVQ = 4;            // pixels per thread and column (vertical)
+constexpr int kVC = 2;            // columns per thread, 32 apart
+constexpr int kVTileX = 32 * kVC; // block (32, 8): 64 columns x 8 thread rows x 4 pixels
+constexpr int kVTileY = 8 * kVQ;  // 32 output rows per CTA
 
 struct ValleyParams {
     const float* dem;  // z-scored DEM
@@ -28,26 +29,26 @@ struct ValleyParams {
     int64_t ld_in, ld_out;
     int nx, gny, in_gy0, in_rows, out_gy0, out_rows;
     const float* bank;        // per angle: [w][hp][4] floats (column-major kernel, 4 channel slots)
-    const int* bank_hw;       // per angle: h, w, hp, reserved
+    const int* bank_hw;       // per angle: h, w, hp, first column's index in bank_cols
+    const int2* bank_cols;    // per kernel column: (lo, n) row range to walk, multiples of 4
     const int64_t* bank_off;  // per angle: element offset into bank
     int n_angles;
     int HT, HB, HL, HR;  // halos: max anchor / max (h-1-anchor) over the angles
     int tile_pitch;
-    int use_smem;
 };
 
-template <int NCH>
+template <int NCH, bool SMEM>
 __global__ void __launch_bounds__(256) valley_kernel(const ValleyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int x0 = blockIdx.x * kVTileX;
     const int y0 = p.out_gy0 + blockIdx.y * kVTileY;  // global row of the tile's first output row
-    const int tile_rows = kVTileY + p.HT + p.HB + 3;
-    const int tile_cols = kVTileX + p.HL + p.HR;
     const int in_end = p.in_gy0 + p.in_rows;
 
-    if (p.use_smem) {
+    if (SMEM) {
+        const int tile_rows = kVTileY + p.HT + p.HB + 3;
+        const int tile_cols = kVTileX + p.HL + p.HR;
         for (int r = ty; r < tile_rows; r += 8) {
             const int gy = y0 - p.HT + r;
             const bool row_ok = gy >= 0 && gy < p.gny && gy >= p.in_gy0 && gy < in_end;
@@ -61,71 +62,88 @@ __global__ void __launch_bounds__(256) valley_kernel(const ValleyParams p) {
         __syncthreads();
     }
 
-    float best[kVQ], bdir[kVQ];
+    float best[kVC][kVQ], bdir[kVC][kVQ];
 #pragma unroll
-    for (int q = 0; q < kVQ; ++q) best[q] = -INFINITY, bdir[q] = 0.f;
+    for (int c = 0; c < kVC; ++c)
+#pragma unroll
+        for (int q = 0; q < kVQ; ++q) best[c][q] = -INFINITY, bdir[c][q] = 0.f;
 
     for (int a = 0; a < p.n_angles; ++a) {
         const int h = p.bank_hw[4 * a], w = p.bank_hw[4 * a + 1], hp = p.bank_hw[4 * a + 2];
+        const int2* cols = p.bank_cols + p.bank_hw[4 * a + 3];
         const float4* wb = reinterpret_cast<const float4*>(p.bank + p.bank_off[a]);
         const int oy = p.HT - h / 2, ox = p.HL - w / 2;  // anchors: h/2, w/2 (flipped kernel)
-        float acc[kVQ][NCH];
+        float acc[kVC][kVQ][NCH];
 #pragma unroll
-        for (int q = 0; q < kVQ; ++q)
+        for (int c = 0; c < kVC; ++c)
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) acc[q][ch] = 0.f;
+            for (int q = 0; q < kVQ; ++q)
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) acc[c][q][ch] = 0.f;
 
         for (int j = 0; j < w; ++j) {
             float4 wr[kVQ];
 #pragma unroll
             for (int q = 0; q < kVQ; ++q) wr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int2 cr = __ldg(cols + j);  // rows [cr.x, cr.x + cr.y) hold every non-zero weight of this column
             const float4* wcol = wb + (int64_t)j * hp;
-            const int col = tx + j + ox;  // tile column
-            for (int s0 = 0; s0 < hp; s0 += kVQ) {
+            const int row0 = ty * kVQ + oy, col = tx + j + ox;  // tile coordinates of the sample under weight row 0
+            const float* tp = tile + (row0 + cr.x) * p.tile_pitch + col;
+            for (int s0 = cr.x; s0 < cr.x + cr.y; s0 += kVQ) {
 #pragma unroll
                 for (int s = 0; s < kVQ; ++s) {
-                    const int si = s0 + s;
 #pragma unroll
                     for (int q = kVQ - 1; q > 0; --q) wr[q] = wr[q - 1];
-                    wr[0] = __ldg(wcol + si);  // rows >= h are zero padding
-                    const int row = ty * kVQ + si + oy;  // tile row; independent of q (sliding window)
-                    float d;
-                    if (p.use_smem) {
-                        d = tile[row * p.tile_pitch + col];
+                    wr[0] = __ldg(wcol + s0 + s);  // rows >= h are zero padding
+                    float d[kVC];
+                    if (SMEM) {
+#pragma unroll
+                        for (int c = 0; c < kVC; ++c) d[c] = tp[32 * c];  // sample row is independent of q (sliding window)
+                        tp += p.tile_pitch;
                     } else {
-                        const int gy = y0 - p.HT + row, gx = x0 - p.HL + col;
-                        d = 0.f;
-                        if (gy >= 0 && gy < p.gny && gy >= p.in_gy0 && gy < in_end && gx >= 0 && gx < p.nx)
-                            d = __ldg(p.dem + (int64_t)(gy - p.in_gy0) * p.ld_in + gx);
+                        const int gy = y0 - p.HT + row0 + s0 + s;
+                        const bool row_ok = gy >= 0 && gy < p.gny && gy >= p.in_gy0 && gy < in_end;
+#pragma unroll
+                        for (int c = 0; c < kVC; ++c) {
+                            const int gx = x0 - p.HL + col + 32 * c;
+                            d[c] = 0.f;
+                            if (row_ok && gx >= 0 && gx < p.nx) d[c] = __ldg(p.dem + (int64_t)(gy - p.in_gy0) * p.ld_in + gx);
+                        }
                     }
 #pragma unroll
-                    for (int q = 0; q < kVQ; ++q) {
-                        acc[q][0] = fmaf(wr[q].x, d, acc[q][0]);
-                        if constexpr (NCH > 1) acc[q][1] = fmaf(wr[q].y, d, acc[q][1]);
-                        if constexpr (NCH > 2) acc[q][2] = fmaf(wr[q].z, d, acc[q][2]);
-                        if constexpr (NCH > 3) acc[q][3] = fmaf(wr[q].w, d, acc[q][3]);
-                    }
+                    for (int c = 0; c < kVC; ++c)
+#pragma unroll
+                        for (int q = 0; q < kVQ; ++q) {
+                            acc[c][q][0] = fmaf(wr[q].x, d[c], acc[c][q][0]);
+                            if constexpr (NCH > 1) acc[c][q][1] = fmaf(wr[q].y, d[c], acc[c][q][1]);
+                            if constexpr (NCH > 2) acc[c][q][2] = fmaf(wr[q].z, d[c], acc[c][q][2]);
+                            if constexpr (NCH > 3) acc[c][q][3] = fmaf(wr[q].w, d[c], acc[c][q][3]);
+                        }
                 }
             }
         }
 #pragma unroll
-        for (int q = 0; q < kVQ; ++q) {
-            float m = acc[q][0];
+        for (int c = 0; c < kVC; ++c)
 #pragma unroll
-            for (int ch = 1; ch < NCH; ++ch) m = fmaxf(m, acc[q][ch]);
-            if (m > best[q]) best[q] = m, bdir[q] = (float)a;
-        }
+            for (int q = 0; q < kVQ; ++q) {
+                float m = acc[c][q][0];
+#pragma unroll
+                for (int ch = 1; ch < NCH; ++ch) m = fmaxf(m, acc[c][q][ch]);
+                if (m > best[c][q]) best[c][q] = m, bdir[c][q] = (float)a;
+            }
     }
 
-    const int x = x0 + tx;
-    if (x < p.nx) {
+#pragma unroll
+    for (int c = 0; c < kVC; ++c) {
+        const int x = x0 + tx + 32 * c;
+        if (x >= p.nx) continue;
 #pragma unroll
         for (int q = 0; q < kVQ; ++q) {
             const int gy = y0 + ty * kVQ + q;
             if (gy < p.out_gy0 + p.out_rows) {
                 const int64_t o = (int64_t)(gy - p.out_gy0) * p.ld_out + x;
-                p.norm[o] = fmaxf(best[q], 0.f);
-                p.dir[o] = bdir[q];
+                p.norm[o] = fmaxf(best[c][q], 0.f);
+                p.dir[o] = bdir[c][q];
             }
         }
     }
@@ -139,8 +157,8 @@ extern "C" {
 
 int topo_valley_ridge_f32(const float* dem_norm, int64_t ld_in, float* norm, float* dir, int64_t ld_out,
                           const topo_view* v, const float* bank, const int* bank_hw, const int64_t* bank_off,
-                          int n_angles, int n_ch, int hmax, int wmax, void* stream) {
-    TOPO_CHECK(dem_norm && norm && dir && bank && bank_hw && bank_off, "null pointer");
+                          const int* bank_cols, int n_angles, int n_ch, int hmax, int wmax, void* stream) {
+    TOPO_CHECK(dem_norm && norm && dir && bank && bank_hw && bank_off && bank_cols, "null pointer");
     if (validate_view(v)) return -1;
     TOPO_CHECK(n_angles >= 1, "no angles");
     TOPO_CHECK(n_ch >= 1 && n_ch <= 4, "flat_list of length %d is not supported (1..4)", n_ch);
@@ -151,6 +169,7 @@ int topo_valley_ridge_f32(const float* dem_norm, int64_t ld_in, float* norm, flo
     p.nx = v->nx, p.gny = v->gny, p.in_gy0 = v->in_gy0, p.in_rows = v->in_rows;
     p.out_gy0 = v->out_gy0, p.out_rows = v->out_rows;
     p.bank = bank, p.bank_hw = bank_hw, p.bank_off = bank_off, p.n_angles = n_angles;
+    p.bank_cols = reinterpret_cast<const int2*>(bank_cols);
     // anchors are h/2, w/2: rows above <= hmax/2; rows below h - 1 - h/2 <= h/2 <= hmax/2 for every h
     p.HT = hmax / 2, p.HB = hmax / 2;
     p.HL = wmax / 2, p.HR = wmax / 2;
@@ -163,15 +182,19 @@ int topo_valley_ridge_f32(const float* dem_norm, int64_t ld_in, float* norm, flo
     const int tile_rows = kVTileY + p.HT + p.HB + 3, tile_cols = kVTileX + p.HL + p.HR;
     p.tile_pitch = tile_cols;
     const size_t smem = (size_t)tile_rows * p.tile_pitch * sizeof(float);
-    p.use_smem = smem <= 200 * 1024;
+    const bool use_smem = smem <= 200 * 1024;
     dim3 grid(ceil_div(v->nx, kVTileX), ceil_div(v->out_rows, kVTileY));
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t dyn = p.use_smem ? smem : 0;
-#define TOPO_VALLEY_LAUNCH(N)                                                                                     \
-    do {                                                                                                          \
-        TOPO_CUDA(cudaFuncSetAttribute(valley_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-        topo::ProfScope prof__("valley_bank", s);                                                                \
-        valley_kernel<N><<<grid, dim3(32, 8), dyn, s>>>(p);                                                       \
+#define TOPO_VALLEY_LAUNCH(N)                                                                                       \
+    do {                                                                                                            \
+        topo::ProfScope prof__("valley_bank", s);                                                                  \
+        if (use_smem) {                                                                                             \
+            TOPO_CUDA(cudaFuncSetAttribute(valley_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                           227 * 1024));                                                            \
+            valley_kernel<N, true><<<grid, dim3(32, 8), smem, s>>>(p);                                              \
+        } else {                                                                                                    \
+            valley_kernel<N, false><<<grid, dim3(32, 8), 0, s>>>(p);                                                \
+        }                                                                                                           \
     } while (0)
     switch (n_ch) {
         case 1: TOPO_VALLEY_LAUNCH(1); break;

@@ -332,5 +332,5 @@ def valley_ridge(dem_norm, bank, out_gy0=None, out_rows=None):
     direction = _new(v.out_rows, dem_norm.nx, dem_norm.tensor)
     _lib.call("topo_valley_ridge_f32", _ptr(dem_norm.tensor), dem_norm.ld, _ptr(norm), _ptr(direction),
               int(norm.stride(0)), ctypes.byref(v), _ptr(bank["data"]), _ptr(bank["hw"]), _ptr(bank["off"]),
-              int(bank["n_angles"]), int(bank["n_ch"]), int(bank["hmax"]), int(bank["wmax"]), _stream())
+              _ptr(bank["cols"]), int(bank["n_angles"]), int(bank["n_ch"]), int(bank["hmax"]), int(bank["wmax"]), _stream())
     return norm, direction

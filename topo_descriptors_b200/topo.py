@@ -231,6 +231,7 @@ def _device_bank(size, mode, flat_list, device):
         bank["data"] = torch.from_numpy(host["data"]).to(device)
         bank["hw"] = torch.from_numpy(host["hw"]).to(device)
         bank["off"] = torch.from_numpy(host["off"]).to(device)
+        bank["cols"] = torch.from_numpy(host["cols"]).to(device)
         if len(_BANK_CACHE) > 16:
             _BANK_CACHE.clear()
         _BANK_CACHE[key] = bank
