@@ -49,6 +49,28 @@ def main():
                     bad += 1
                     d = (got[(name, i)] - r[ctx.r0 : ctx.r1]).abs().max().item()
                     print(f"rank {rank}: MISMATCH {name} size {size} integer={integer} max diff {d}", flush=True)
+    # valley / ridge and Sx bands (z-score statistics are reduced per band: equal up to the float32 rounding of
+    # mean / std, so compare with a tolerance and count direction flips)
+    from topo_descriptors_b200 import topo  # noqa: E402
+    from topo_descriptors_b200.synth import dem_dataset  # noqa: E402
+
+    z = fractal_dem(ny, nx, seed=6)
+    whole = DeviceDEM(torch.from_numpy(z).to(device))
+    ctx = bands.BandContext(ny, nx, rank, world)
+    core = whole.tensor[ctx.r0 : ctx.r1].contiguous()
+    for sigma in (None, 2.25):
+        want = topo.valley_ridge(whole, 21, "valley", [0, 0.15, 0.3], sigma)
+        n, d = bands.valley_ridge_band(core, ctx, 21, "valley", [0, 0.15, 0.3], sigma)
+        dn = (n - want[0][ctx.r0 : ctx.r1]).abs().max().item()
+        flips = (d != want[1][ctx.r0 : ctx.r1]).float().mean().item()
+        if dn > 1e-4 or flips > 1e-3:
+            bad += 1
+            print(f"rank {rank}: MISMATCH valley_ridge sigma={sigma} norm diff {dn} direction flips {flips}", flush=True)
+    plan = topo._sx_plan(dem_dataset(z, res=25.0), [45.0, 200.0], 2000.0, 10.0, 15, 0.0)
+    ref = topo._sx_device(whole, plan, 10.0)
+    if not torch.equal(bands.sx_band(core, ctx, plan, 10.0), ref[:, ctx.r0 : ctx.r1]):
+        bad += 1
+        print(f"rank {rank}: MISMATCH sx band", flush=True)
     t = torch.tensor([bad], device=device)
     dist.all_reduce(t)
     if rank == 0:

@@ -382,6 +382,40 @@ def test_bands_bit_identical():
         assert (dev.gauss(band, sigma, sigma, lo, hi - lo) == ref_g[lo:hi]).all()
 
 
+def test_bands_valley_sx_bit_identical():
+    """Row bands of valley_ridge and Sx equal the same rows of the whole-image result."""
+    from topo_descriptors_b200 import bands
+
+    z = fractal_dem(301, 420, seed=13)
+    ds = dem_dataset(z, res=30.0)
+    whole = DeviceDEM(dev.to_device(z))
+    cuts = [0, 97, 200, 301]
+    # valley / ridge through the band entry point (world 1 = whole image) and through band views
+    ctx = bands.BandContext(301, 420)
+    for sigma in (None, 1.5):
+        want = topo.valley_ridge(z, 9, "valley", [0, 0.15, 0.3], sigma)
+        got = bands.valley_ridge_band(whole.tensor, ctx, 9, "valley", [0, 0.15, 0.3], sigma)
+        assert np.array_equal(got[0].cpu().numpy(), want[0]) and np.array_equal(got[1].cpu().numpy(), want[1])
+    st = whole.stats
+    mean = st["sum"] / st["n"]
+    sd = np.sqrt(st["sumsq"] / st["n"] - mean * mean)
+    normed = dev.zscore(whole, np.float32(mean), np.float32(sd))
+    bank = topo._device_bank(9, "valley", [0, 0.15, 0.3], whole.tensor.device)
+    ref_n, ref_d = dev.valley_ridge(normed, bank)
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        band = _band(normed.tensor, lo, hi, bank["hmax"] // 2, st)
+        n, d = dev.valley_ridge(band, bank, lo, hi - lo)
+        assert (n == ref_n[lo:hi]).all() and (d == ref_d[lo:hi]).all()
+    # Sx
+    plan = topo._sx_plan(ds, [0.0, 135.0, 270.0], 300.0, 10.0, 15, 0.0)
+    ref = topo._sx_device(whole, plan, 10.0)
+    assert (bands.sx_band(whole.tensor, ctx, plan, 10.0) == ref).all()
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        band = _band(whole.tensor, lo, hi, plan[3], None)
+        assert (topo._sx_device(band, plan, 10.0, lo, hi - lo) == ref[:, lo:hi]).all()
+    assert bands.azimuth_share(range(10), bands.BandContext(10, 4, 1, 4)) == [1, 5, 9]
+
+
 # ---------------------------------------------------------------------------------------------
 # compute_* drivers
 # ---------------------------------------------------------------------------------------------

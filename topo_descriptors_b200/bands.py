@@ -161,6 +161,62 @@ def sweep(core, ctx, sizes, sigmas, res_x, res_y, what=("tpi", "std", "gradient"
     return calls
 
 
+# ---------------------------------------------------------------------------------------------
+# valley / ridge and Sx on one band
+# ---------------------------------------------------------------------------------------------
+def valley_ridge_band(core, ctx, size, mode, flat_list=(0, 0.15, 0.3), sigma=None):
+    """Valley / ridge norm and direction for this rank's rows (reference topo.py:389-453).
+
+    Halo = half the tallest rotated kernel (+ the Gaussian radius when ``sigma`` pre-smooths); the z-score
+    uses the GLOBAL mean / std of the (smoothed) DEM: every rank reduces its own rows, one all-reduce.
+    Returns (norm, direction) tensors of shape (rows, nx).
+    """
+    from . import device as dev, topo
+    from .device import DeviceDEM
+
+    bank = topo._device_bank(size, mode, list(flat_list), core.device)
+    khalo = int(bank["hmax"]) // 2
+    lw = dev.gauss_radius(sigma) if sigma else 0
+    band, gy0 = exchange_halo(core, ctx, khalo + lw)
+    raw_stats = global_stats(dev.dem_stats(core), ctx, device=core.device)
+    ddem = DeviceDEM(band, gny=ctx.gny, gy0=gy0, stats=raw_stats)
+    s0, s1 = ctx.halo_extent(khalo)  # rows of the (smoothed) DEM the kernels read
+    if sigma:
+        smooth = dev.gauss(ddem, sigma, sigma, s0, s1 - s0)
+        own = smooth[ctx.r0 - s0 : ctx.r1 - s0]
+        stats = global_stats(dev.dem_stats(own), ctx, device=core.device)
+        src = DeviceDEM(smooth, gny=ctx.gny, gy0=s0, stats=stats)
+    else:
+        stats = raw_stats
+        src = DeviceDEM(band[s0 - gy0 : s1 - gy0], gny=ctx.gny, gy0=s0, stats=stats)
+    if stats["nonfinite"] > 0:  # the reference's FFT spreads NaN everywhere: norm = clip(-inf) = 0 (topo.py:441-452)
+        zero = dev._new(ctx.rows, ctx.nx, core)
+        dev.fill(zero, 0.0)
+        return zero, zero.clone()
+    mean64 = stats["sum"] / stats["n"]
+    var64 = max(stats["sumsq"] / stats["n"] - mean64 * mean64, 0.0)
+    normed = dev.zscore(src, np.float32(mean64), np.float32(np.sqrt(var64)))
+    return dev.valley_ridge(normed, bank, ctx.r0, ctx.rows)
+
+
+def sx_band(core, ctx, plan, height=10.0):
+    """Sx for this rank's rows and every azimuth of ``plan`` (topo._sx_plan): halo = the sample window.
+    Returns a tensor (n_azimuths, rows, nx).  (For many azimuths on a DEM that fits one GPU, dealing the
+    azimuths round-robin -- ``azimuth_share`` -- needs no communication at all.)"""
+    from . import topo
+    from .device import DeviceDEM
+
+    window = int(plan[3])
+    band, gy0 = exchange_halo(core, ctx, window)
+    ddem = DeviceDEM(band, gny=ctx.gny, gy0=gy0)
+    return topo._sx_device(ddem, plan, height, ctx.r0, ctx.rows)
+
+
+def azimuth_share(azimuths, ctx):
+    """Round-robin deal of independent work items (azimuths, scales) over the ranks."""
+    return list(azimuths)[ctx.rank :: ctx.world]
+
+
 def numpy_partition_check(gny, world):
     """Small self-check used by the tests: the partition tiles [0, gny) without gaps."""
     parts = partition_rows(gny, world)
