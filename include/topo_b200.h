@@ -68,6 +68,23 @@ int topo_fill_f32(float* out, int rows, int nx, int64_t ld, float value, void* s
 int topo_stamp_f32(float* out, int64_t ld, const int* rows, const int* cols, int64_t n, float value,
                    void* stream);
 
+/* ---- pre-stage (helpers.py:17-31, 137-154): mask + NaN census + nearest-neighbour fill along x -------
+ * A cell is MISSING when it is NaN, or -- with use_mask -- when it is <= mask_below
+ * (`dem.where(dem > CFG.min_elevation)`, helpers.py:31).
+ * topo_fill_na_f32: out = dem with every missing cell replaced by the valid cell of its row nearest in x
+ *   (`interpolate_na(dim="x", method="nearest", fill_value="extrapolate")`, helpers.py:152-154: scipy
+ *   interp1d "nearest" -- exact half-way points take the lower-x neighbour, cells beyond the first / last
+ *   valid one take that one, rows without a valid cell stay NaN).  x (DEVICE, optional): the nx x-coordinates;
+ *   NULL = uniform ascending grid.  row_missing (DEVICE, optional, `rows` ints): missing cells per row.
+ * topo_nan_indices_f32: `ind_nans = np.where(np.isnan(dem))` (helpers.py:150) in row-major order.
+ *   Call 1 (out_rows = out_cols = NULL): row_offsets[0..rows] = exclusive prefix sum of row_missing
+ *   (row_offsets[rows] = total: the caller reads it and sizes the outputs).  Call 2: fills out_rows / out_cols. */
+int topo_fill_na_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int rows, int nx,
+                     const double* x, int use_mask, float mask_below, int* row_missing, void* stream);
+int topo_nan_indices_f32(const float* dem, int64_t ld_in, int rows, int nx, int use_mask, float mask_below,
+                         const int* row_missing, int64_t* row_offsets, int* out_rows, int* out_cols,
+                         void* stream);
+
 /* ---- TPI (topo.py:144-181) and STD (topo.py:272-307): disc sums ------------------------------
  * Zero-padded "same" convolution with circular_kernel(size) (topo.py:191-213; a square for
  * size < 5), scipy centring for even sizes.  Per-row prefix sums in 32-bit fixed point

@@ -417,6 +417,60 @@ def test_bands_valley_sx_bit_identical():
 
 
 # ---------------------------------------------------------------------------------------------
+# device pre-stage: mask + NaN census + nearest fill (helpers.py:17-31, 137-154)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(40, 97), (33, 1000), (7, 31), (3, 4099)])
+def test_fill_na_resident(shape):
+    from topo_descriptors_b200 import prestage
+
+    rng = np.random.default_rng(shape[1])
+    z = rng.uniform(-50, 1000, shape).astype(np.float32)
+    z[rng.uniform(size=shape) < 0.3] = np.nan
+    z[1, :] = np.nan                      # a row without any valid cell stays NaN
+    z[2, :] = np.nan
+    z[2, shape[1] // 2] = 3.0             # a single valid cell fills its row
+    z[0, : shape[1] * 2 // 3] = np.nan    # long gaps at both ends
+    z[min(4, shape[0] - 1), shape[1] // 3 :] = np.nan
+    base = dem_dataset(z, res=30.0)
+    xs = base["x"].values
+    warped = xs + 7.0 * np.sin(np.arange(xs.size))  # non-uniform but still ascending coordinates
+    for x, thr in ((xs, None), (xs[::-1].copy(), None), (warped, None), (xs, 100.0)):
+        ds = _xr.Dataset({"alti": (("y", "x"), z)}, coords={"x": x, "y": base["y"].values}, attrs=base.attrs)
+        ind, filled = prestage.fill_na_resident(ds, mask_below=thr)
+        want_ind, want = O.fill_na_exact(z, x, thr)
+        assert np.array_equal(ind[0].cpu().numpy(), want_ind[0]) and np.array_equal(ind[1].cpu().numpy(), want_ind[1])
+        got = hlp.get_da(filled).values
+        assert isinstance(got, DeviceDEM)
+        assert np.array_equal(got.numpy(), want, equal_nan=True)
+    # nothing missing: identity and empty index tensors
+    clean = np.nan_to_num(z, nan=5.0)
+    ind, filled = prestage.fill_na_resident(dem_dataset(clean, res=30.0))
+    assert ind[0].numel() == 0 and np.array_equal(hlp.get_da(filled).values.numpy(), clean)
+
+
+def test_compute_driver_on_resident_dataset(tmp_path):
+    """The script's pipeline with the DEM resident from the pre-stage on equals the host-marshalled one."""
+    from topo_descriptors_b200 import prestage
+
+    z = fractal_dem(120, 160, seed=22)
+    z[5, 7] = np.nan
+    z[60, 61:90] = np.nan
+    ds = dem_dataset(z, res=30.0)
+    ind_h, ds_h = hlp.fill_na(ds)
+    ind_d, ds_d = prestage.fill_na_resident(ds)
+    (tmp_path / "h").mkdir()
+    (tmp_path / "d").mkdir()
+    for ind, d, out in ((ind_h, ds_h, tmp_path / "h"), (ind_d, ds_d, tmp_path / "d")):
+        topo.compute_tpi(d, [200, 500], ind_nans=ind, outdir=out)
+        topo.compute_gradient(d, [200], ind_nans=ind, outdir=out)
+        topo.compute_sx(d, 0, 150, outdir=out)
+    for f in sorted((tmp_path / "h").iterdir()):
+        with np.load(f) as a, np.load(tmp_path / "d" / f.name) as b:
+            for k in a.files:
+                assert np.array_equal(a[k], b[k], equal_nan=a[k].dtype.kind == "f"), (f.name, k)
+
+
+# ---------------------------------------------------------------------------------------------
 # compute_* drivers
 # ---------------------------------------------------------------------------------------------
 def test_compute_drivers(tmp_path, c1):

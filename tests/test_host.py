@@ -187,6 +187,26 @@ def test_fill_na_nearest():
     assert f[0, 0] == 2 and f[0, 1] == 2 and f[1, 3] == 10 and f[2, 6] == 21 and f[2, 7] == 21
 
 
+def test_fill_na_matches_scipy_nearest():
+    """helpers.fill_na against the oracle's scipy interp1d('nearest', extrapolate) restatement of xarray's
+    interpolate_na: long gaps, all-NaN rows, a single valid cell, both coordinate orders."""
+    rng = np.random.default_rng(0)
+    z = rng.uniform(0, 1000, (40, 97)).astype(np.float32)
+    z[rng.uniform(size=z.shape) < 0.3] = np.nan
+    z[5, :] = np.nan
+    z[6, :] = np.nan
+    z[6, 50] = 3.0
+    z[7, :40] = np.nan
+    z[8, 60:] = np.nan
+    base = dem_dataset(z, res=30.0)
+    for x in (base["x"].values, base["x"].values[::-1].copy()):
+        ds = _xr.Dataset({"alti": (("y", "x"), z)}, coords={"x": x, "y": base["y"].values}, attrs=base.attrs)
+        ind, filled = hlp.fill_na(ds)
+        want_ind, want = O.fill_na_exact(z, x)
+        assert np.array_equal(ind[0], want_ind[0]) and np.array_equal(ind[1], want_ind[1])
+        assert np.array_equal(hlp.get_da(filled).values, want, equal_nan=True)
+
+
 def test_to_netcdf_npz_sink(tmp_path):
     z = fractal_dem(12, 16, seed=1)
     ds = dem_dataset(z, res=30.0)
@@ -197,6 +217,13 @@ def test_to_netcdf_npz_sink(tmp_path):
     with np.load(p) as f:
         assert f["TPI_200M"].shape == (6, 8) and np.array_equal(f["TPI_200M"], (z * 2)[3:9, 2:10])
         assert str(f["units"]) == "m" and np.array_equal(f["x"], x[2:10])
+    # the same crop applied before the copy back (device-side crop of the compute_* drivers)
+    w = ds.sel_window(crop)
+    assert w == {"x": (2, 10), "y": (3, 9)}
+    p2 = hlp.to_netcdf((z * 2)[3:9, 2:10], ds, "tpi_300m", crop, tmp_path, "m", window=w)
+    with np.load(p) as f, np.load(p2) as g:
+        assert np.array_equal(f["TPI_200M"], g["TPI_300M"]) and np.array_equal(f["y"], g["y"]) and np.array_equal(f["x"], g["x"])
+    assert ds.sel_window({"x": slice(x[-1] + 1, None)}) == {"x": (0, 0)}
 
 
 # ---- the C-ABI library --------------------------------------------------------------------------------

@@ -57,6 +57,10 @@ PROTOTYPES = {
                                         c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "topo_sx_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, _VP, c_void_p, c_void_p, c_void_p,
                             c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "topo_fill_na_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_float, c_void_p,
+                                 c_void_p]),
+    "topo_nan_indices_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
     "topo_zscore_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_float, c_void_p]),
     "topo_valley_ridge_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, _VP, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

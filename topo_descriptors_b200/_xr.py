@@ -19,7 +19,8 @@ class DataArray:
     """Minimal labelled array: ``values``/``data``, ``dims``, ``attrs``."""
 
     def __init__(self, values, dims=(), attrs=None):
-        self.values = np.asarray(values)
+        # a device-resident DEM (device.DeviceDEM) is kept as it is: the pre-stage hands such Datasets to compute_*
+        self.values = values if getattr(values, "is_device_dem", False) else np.asarray(values)
         self.dims = tuple(dims)
         self.attrs = dict(attrs or {})
 
@@ -92,6 +93,29 @@ class Dataset:
             self._vars[name] = spec
         else:
             self._vars[name] = DataArray(spec[1], spec[0])
+
+    def sel_window(self, indexers=None):
+        """The index ranges ``{dim: (start, stop)}`` that ``sel`` keeps, or None when a selection is not one
+        contiguous run (non-monotonic coordinate).  Lets the drivers crop on the device before the D2H copy."""
+        out = {}
+        for name, sl in (indexers or {}).items():
+            c = self.coords[name].values
+            if not isinstance(sl, slice):
+                raise TypeError("only slice indexers are supported")
+            asc = c.size < 2 or c[-1] >= c[0]
+            keep = np.ones(c.shape, dtype=bool)
+            if sl.start is not None:
+                keep &= (c >= sl.start) if asc else (c <= sl.start)
+            if sl.stop is not None:
+                keep &= (c <= sl.stop) if asc else (c >= sl.stop)
+            idx = np.nonzero(keep)[0]
+            if idx.size == 0:
+                out[name] = (0, 0)
+            elif idx[-1] - idx[0] + 1 != idx.size:
+                return None
+            else:
+                out[name] = (int(idx[0]), int(idx[-1]) + 1)
+        return out
 
     def sel(self, indexers=None):
         """Label-based crop with ``{coord: slice(lo, hi)}`` like ``xr.Dataset.sel`` (helpers.py:57-59).

@@ -807,6 +807,12 @@ struct PairAcc {
     unsigned long long s64[kRB][2];
 };
 
+// Stops the compiler from folding a row base back into every per-lookup address computation.
+__device__ __forceinline__ const uint32_t* opaque_ptr(const uint32_t* p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
+
 template <bool ACC32>
 __device__ __forceinline__ void pair_add(PairAcc& A, int b, const uint2 hv, const uint2 lv) {
     if (ACC32) {
@@ -830,17 +836,22 @@ __device__ __forceinline__ void row_walk_grouped(const DiscParams& p, const int*
                                                  int i_begin, int i_end, int lead, int lag, PairAcc& A) {
     const int pitch = p.pitch;
     const int pstride = (int)p.plane_stride;  // host guarantees it fits 31 bits
-    int offR[kRB], offL[kRB];
-    auto fetch = [&](int i, int& oR, int& oL) {
+    // Element offsets INCLUDING the thread's column, kept unsigned: the address of a lookup is then
+    // row base (64-bit, shared by the 16 loads of a step) + 4 * offset = ONE IMAD.WIDE.U32 on the FMA pipe.
+    // (Signed offsets added to a per-thread pointer cost 4 ALU-pipe instructions per load and made this walk
+    // ALU-bound: ncu 79% ALU pipe, profiles/r01_ncu_full_summary.csv.)
+    const uint32_t ulcx = (uint32_t)lcx;
+    uint32_t offR[kRB], offL[kRB];
+    auto fetch = [&](int i, uint32_t& oR, uint32_t& oL) {
         if (i >= i_begin && i < i_end) {
             const int e = tab[i];
             const int lo = (int)(short)(e & 0xffff);
             const int hi1 = (e >> 16) + 1;
             // lcx is even: parity of the element index = parity of the offset; odd -> shifted copy B
-            oR = (hi1 & 1) ? (pstride + hi1 - 1) : hi1;
-            oL = (lo & 1) ? (pstride + lo - 1) : lo;
+            oR = ulcx + (uint32_t)((hi1 & 1) ? (pstride + hi1 - 1) : hi1);
+            oL = ulcx + (uint32_t)((lo & 1) ? (pstride + lo - 1) : lo);
         } else {
-            oR = 0, oL = 0;  // both loads hit the same word: contributes 0
+            oR = ulcx, oL = ulcx;  // both loads hit the same word: contributes 0
         }
     };
     const int t0 = i_begin - (kRB - 1) - lead;
@@ -854,7 +865,7 @@ __device__ __forceinline__ void row_walk_grouped(const DiscParams& p, const int*
             if (t + s + kRB > i_begin && t + s < i_end) {  // some slot i = t+s+b is valid (warp-uniform)
                 int r = R0 - (t + s);  // slots outside the range carry zero contributions: keep them in bounds
                 r = r < 0 ? 0 : (r > last_row ? last_row : r);
-                const uint32_t* rowp = p.planes + (int64_t)r * pitch + lcx;
+                const uint32_t* rowp = opaque_ptr(p.planes + (int64_t)r * pitch);
 #pragma unroll
                 for (int b = 0; b < kRB; ++b) {
                     const uint2 hv = __ldg(reinterpret_cast<const uint2*>(rowp + offR[b]));
@@ -895,21 +906,26 @@ __device__ __forceinline__ void hybrid_walk(const DiscParams& p, const int* __re
     }
     // ---- left / right caps: columns |cc| > a, column-prefix spans of half-height h = half-width of row mid+cc
     if (!(p.dbg_skip & 1)) {
-        const uint32_t* colp = p.cplanes + (int64_t)prow * pitch + lcx;
+        const uint32_t* colp = p.cplanes + (int64_t)prow * pitch;  // row base; the column goes into the offset
         const int cstride = (int)p.cplane_stride;
 #pragma unroll 1
         for (int cc = a_sq + 1; cc <= mid; ++cc) {
             const int h = tab[mid + cc] >> 16;  // dxhi of kernel row mid+cc = its half-width (odd size)
-            const int up = -h * pitch, dn = (h + 1) * pitch;
+            const uint32_t* up = colp - (int64_t)h * pitch;
+            const uint32_t* dn = colp + (int64_t)(h + 1) * pitch;
+            const uint32_t* upb[kRB];
+            const uint32_t* dnb[kRB];
+#pragma unroll
+            for (int b = 0; b < kRB; ++b) upb[b] = opaque_ptr(up + (int64_t)b * pitch), dnb[b] = opaque_ptr(dn + (int64_t)b * pitch);
 #pragma unroll
             for (int sgn = 0; sgn < 2; ++sgn) {
                 const int c = sgn ? cc : -cc;
-                const int oc = (c & 1) ? (cstride + c - 1) : c;  // lcx even: parity of the column = parity of c
+                // lcx even: parity of the column = parity of c; unsigned element offset -> IMAD.WIDE.U32 addressing
+                const uint32_t oc = (uint32_t)(lcx + ((c & 1) ? (cstride + c - 1) : c));
 #pragma unroll
                 for (int b = 0; b < kRB; ++b) {
-                    const uint32_t* q = colp + (int64_t)b * pitch + oc;
-                    const uint2 hv = __ldg(reinterpret_cast<const uint2*>(q + dn));
-                    const uint2 lv = __ldg(reinterpret_cast<const uint2*>(q + up));
+                    const uint2 hv = __ldg(reinterpret_cast<const uint2*>(dnb[b] + oc));
+                    const uint2 lv = __ldg(reinterpret_cast<const uint2*>(upb[b] + oc));
                     pair_add<ACC32>(A, b, hv, lv);
                 }
             }

@@ -70,6 +70,20 @@ class DeviceDEM:
         self.gny = int(self.rows if gny is None else gny)
         self._stats = stats
 
+    is_device_dem = True  # lets the Dataset container keep it as the values of the DEM variable
+
+    @property
+    def shape(self):
+        return (self.rows, self.nx)
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    def numpy(self):
+        """One D2H copy of the band."""
+        return self.tensor.cpu().numpy()
+
     @property
     def is_whole(self):
         return self.gy0 == 0 and self.rows == self.gny
@@ -122,6 +136,31 @@ def _new(rows, nx, like):
 
 def fill(t, value):
     _lib.call("topo_fill_f32", _ptr(t), int(t.shape[0]), int(t.shape[1]), int(t.stride(0)), float(value), _stream())
+
+
+def fill_na(tensor, x_dev=None, mask_below=None, want_indices=True):
+    """Device pre-stage of helpers.py:17-31 + 137-154: cells that are NaN (or <= ``mask_below``) are replaced by
+    the nearest valid cell of their row (ties: lower x).  Returns (filled tensor, (rows, cols) int32 device
+    tensors of the missing cells in np.where order or None, number of missing cells)."""
+    torch = require_cuda()
+    rows, nx = int(tensor.shape[0]), int(tensor.shape[1])
+    out = torch.empty((rows, nx), dtype=torch.float32, device=tensor.device)
+    counts = torch.empty((max(rows, 1),), dtype=torch.int32, device=tensor.device)
+    use_mask = 0 if mask_below is None else 1
+    thr = 0.0 if mask_below is None else float(mask_below)
+    _lib.call("topo_fill_na_f32", _ptr(tensor), int(tensor.stride(0)), _ptr(out), int(out.stride(0)), rows, nx,
+              _ptr(x_dev), use_mask, thr, _ptr(counts), _stream())
+    offsets = torch.empty((rows + 1,), dtype=torch.int64, device=tensor.device)
+    _lib.call("topo_nan_indices_f32", _ptr(tensor), int(tensor.stride(0)), rows, nx, use_mask, thr, _ptr(counts),
+              _ptr(offsets), None, None, _stream())
+    total = int(offsets[-1].item())
+    if not want_indices or total == 0:
+        return out, None, total
+    r = torch.empty((total,), dtype=torch.int32, device=tensor.device)
+    c = torch.empty((total,), dtype=torch.int32, device=tensor.device)
+    _lib.call("topo_nan_indices_f32", _ptr(tensor), int(tensor.stride(0)), rows, nx, use_mask, thr, _ptr(counts),
+              _ptr(offsets), _ptr(r), _ptr(c), _stream())
+    return out, (r, c), total
 
 
 def stamp(t, rows_dev, cols_dev, value=float("nan")):

@@ -173,8 +173,11 @@ def get_dem_netcdf(path_dem):
     return dem_ds.where(dem_ds > CFG.min_elevation)  # pragma: no cover
 
 
-def to_netcdf(array, dem_ds, name, crop=None, outdir=".", units=None):
+def to_netcdf(array, dem_ds, name, crop=None, outdir=".", units=None, window=None):
     """Save one descriptor array with the DEM's coordinates and attributes (helpers.py:34-65).
+
+    ``window`` = ``{dim: (start, stop)}`` (from ``Dataset.sel_window(crop)``) says that ``array`` was already
+    cropped on the device: only the coordinates are cut here.
 
     File name ``topo_<NAME>.nc`` with NAME upper-cased.  With real xarray inputs the file is a
     NetCDF written by xarray; with the built-in Dataset container the same content goes to
@@ -192,7 +195,14 @@ def to_netcdf(array, dem_ds, name, crop=None, outdir=".", units=None):
         path = outdir / f"topo_{name}.nc"
         ds.to_netcdf(path)
     else:
-        ds = _xr.Dataset({name: (dims, array)}, coords=dem_ds.coords, attrs=dem_ds.attrs).sel(crop)
+        if window is not None:
+            coords = {}
+            for cname, c in dem_ds.coords.items():
+                lo, hi = window.get(cname, (0, c.values.shape[0]))
+                coords[cname] = _xr.DataArray(c.values[lo:hi], c.dims, c.attrs)
+            ds = _xr.Dataset({name: (dims, array)}, coords=coords, attrs=dem_ds.attrs)
+        else:
+            ds = _xr.Dataset({name: (dims, array)}, coords=dem_ds.coords, attrs=dem_ds.attrs).sel(crop)
         if units is not None:
             ds[name].attrs.update(units=units)
         path = outdir / f"topo_{name}.npz"

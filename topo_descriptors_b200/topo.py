@@ -450,20 +450,30 @@ def _resident(dem_ds, ind_nans):
     """Upload the DEM once for all scales; upload the NaN re-stamp indices once (topo.py:129,139)."""
     import torch
 
-    ddem = DeviceDEM(dev.to_device(hlp.get_da(dem_ds).values))
+    values = hlp.get_da(dem_ds).values
+    ddem = values if isinstance(values, DeviceDEM) else DeviceDEM(dev.to_device(values))
     nans = None
     if ind_nans is not None and len(ind_nans) == 2 and len(ind_nans[0]):
-        rows = torch.from_numpy(np.ascontiguousarray(ind_nans[0], dtype=np.int32)).to(ddem.tensor.device)
-        cols = torch.from_numpy(np.ascontiguousarray(ind_nans[1], dtype=np.int32)).to(ddem.tensor.device)
-        nans = (rows, cols)
+        if torch.is_tensor(ind_nans[0]):  # already on the device (prestage.fill_na_resident)
+            nans = (ind_nans[0].to(torch.int32), ind_nans[1].to(torch.int32))
+        else:
+            rows = torch.from_numpy(np.ascontiguousarray(ind_nans[0], dtype=np.int32)).to(ddem.tensor.device)
+            cols = torch.from_numpy(np.ascontiguousarray(ind_nans[1], dtype=np.int32)).to(ddem.tensor.device)
+            nans = (rows, cols)
     return ddem, nans
 
 
 def _finish_output(tensor, nans, dem_ds, name, crop, outdir, units, dtype=np.float32):
-    """``array[ind_nans] = np.nan`` on device, one D2H, then the reference's writer."""
+    """``array[ind_nans] = np.nan`` and the crop on the device, one D2H of what is kept, then the reference's
+    writer (topo.py:139-140 + helpers.py:57-59)."""
     if nans is not None:
         dev.stamp(tensor, nans[0], nans[1])
+    window = dem_ds.sel_window(crop) if crop and isinstance(dem_ds, _xr.Dataset) else None
+    if window is not None:
+        dims = hlp.get_da(dem_ds).dims
+        (r0, r1), (c0, c1) = (window.get(d, (0, n)) for d, n in zip(dims, tensor.shape))
+        tensor = tensor[r0:r1, c0:c1]
     array = tensor.cpu().numpy()
     if array.dtype != dtype:
         array = array.astype(dtype)
-    hlp.to_netcdf(array, dem_ds, name, crop, outdir, units)
+    hlp.to_netcdf(array, dem_ds, name, crop, outdir, units, window=window)
