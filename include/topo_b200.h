@@ -40,6 +40,20 @@ typedef struct topo_view {
     int out_rows; /* rows to compute */
 } topo_view;
 
+/* Prefix planes shared by the tpi / std calls of ONE DEM band at several sizes (a multi-scale sweep): the
+ * planes of trunc(z) - tmin and of its centred square do not depend on the disc size, so they are built by the
+ * first call that needs them and reused by the later ones (integer-valued DEMs, two-pass sizes).
+ * The caller owns `mem` (DEVICE, 256-byte aligned, >= topo_disc_cache_bytes(v, max_size)), starts with
+ * valid = 0 and passes the same struct, DEM, view and range to every call; the input band must cover the halo
+ * of max_size.  NULL (or mem = NULL) = no sharing. */
+typedef struct topo_disc_cache {
+    void* mem;
+    size_t bytes;
+    int max_size; /* the planes are laid out for discs up to this size */
+    int valid;    /* in/out: bit 0 / 1 = row prefix / column prefix + summed-area table of trunc(z) - tmin,
+                     bit 2 / 3 = the same for the squares plane */
+} topo_disc_cache;
+
 /* ---- library ------------------------------------------------------------------------------ */
 int topo_version(void);
 const char* topo_last_error(void);
@@ -103,12 +117,13 @@ size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi,
  * the first call can keep them (tsum_op = 1, tsum = out_rows*nx uint64 on the DEVICE) and the second reuse
  * them (tsum_op = 2), which removes one of the three gather passes of a tpi+std pair.  tsum_op = 0: off. */
 int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer);
+size_t topo_disc_cache_bytes(const topo_view* v, int max_size);
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
                  int size, int all_integer, double zmin, double zmax, unsigned long long* tsum,
-                 int tsum_op, void* ws, size_t ws_bytes, void* stream);
+                 int tsum_op, topo_disc_cache* cache, void* ws, size_t ws_bytes, void* stream);
 int topo_std_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
                  int size, int all_integer, double zmin, double zmax, unsigned long long* tsum,
-                 int tsum_op, void* ws, size_t ws_bytes, void* stream);
+                 int tsum_op, topo_disc_cache* cache, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Gaussian smoothing (topo.py:62-80; scipy.ndimage.gaussian_filter semantics) -------------
  * Separable, radius int(4*sigma+0.5), float64 weights and accumulation, axis 0 then axis 1 with a

@@ -178,6 +178,30 @@ def test_tpi_std_share_disc_sums():
         assert maxdiff(s1.cpu().numpy(), O.std_exact(zi, size)) <= TOL_M
 
 
+def test_disc_plane_cache_is_transparent():
+    """A multi-scale sweep shares the size-independent prefix planes: identical to the unshared calls, in any
+    order of sizes, for odd (hybrid), even and fused sizes, whole images and row bands."""
+    zi = fractal_dem(450, 520, seed=15, integer=True)
+    plain = DeviceDEM(dev.to_device(zi))
+    sizes = [151, 7, 201, 120, 301, 33]
+    want = {s: (dev.tpi(plain, s, share=False), dev.std(plain, s, share=False)) for s in sizes}
+    shared = DeviceDEM(dev.to_device(zi)).share_disc_planes(max(sizes))
+    for s in sizes:
+        assert bool((dev.tpi(shared, s) == want[s][0]).all()) and bool((dev.std(shared, s) == want[s][1]).all()), s
+    assert shared._plane_cache is not None and shared._plane_cache[1].valid == 15
+    shared.release_disc_planes()
+    # a row band with enough halo for the largest size
+    lo, hi, halo = 120, 300, max(sizes) // 2
+    band = _band(plain.tensor, lo, hi, halo, plain.stats).share_disc_planes(max(sizes))
+    for s in (201, 151, 301):
+        assert bool((dev.std(band, s, lo, hi - lo) == want[s][1][lo:hi]).all()), s
+        assert bool((dev.tpi(band, s, lo, hi - lo) == want[s][0][lo:hi]).all()), s
+    # float DEMs do not use the cache (their planes depend on the size): still correct
+    z = fractal_dem(300, 340, seed=16)
+    f = DeviceDEM(dev.to_device(z)).share_disc_planes(201)
+    assert maxdiff(dev.tpi(f, 201).cpu().numpy(), O.tpi_exact(z, 201)) <= TOL_M and getattr(f, "_plane_cache", None) is None
+
+
 def test_std_sigma(golden):
     got = topo.std(golden["in__zc"], 7, sigma=1.75)
     assert maxdiff(got, O.std_exact(golden["in__zc"], 7, sigma=1.75)) <= TOL_M

@@ -31,6 +31,15 @@ class View(ctypes.Structure):
 
 _VP = POINTER(View)
 
+
+class DiscCache(ctypes.Structure):
+    """``topo_disc_cache`` (include/topo_b200.h): prefix planes shared by tpi / std calls at several sizes."""
+
+    _fields_ = [("mem", c_void_p), ("bytes", c_size_t), ("max_size", c_int), ("valid", c_int)]
+
+
+_CP = POINTER(DiscCache)
+
 # name -> (restype, argtypes); mirrors include/topo_b200.h declaration by declaration
 PROTOTYPES = {
     "topo_version": (c_int, []),
@@ -44,10 +53,11 @@ PROTOTYPES = {
     "topo_stamp_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "topo_disc_workspace_bytes": (c_size_t, [_VP, c_int, c_int]),
     "topo_disc_shares_tsum": (c_int, [_VP, c_int, c_int]),
+    "topo_disc_cache_bytes": (c_size_t, [_VP, c_int]),
     "topo_tpi_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_int, c_int, c_double, c_double,
-                             c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+                             c_void_p, c_int, _CP, c_void_p, c_size_t, c_void_p]),
     "topo_std_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_int, c_int, c_double, c_double,
-                             c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+                             c_void_p, c_int, _CP, c_void_p, c_size_t, c_void_p]),
     "topo_gauss_workspace_bytes": (c_size_t, [_VP, c_int, c_int]),
     "topo_gauss_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_void_p, c_int, c_void_p, c_int, c_int,
                                c_void_p, c_size_t, c_void_p]),

@@ -132,6 +132,8 @@ def sweep(core, ctx, sizes, sigmas, res_x, res_y, what=("tpi", "std", "gradient"
     if stats is None:
         stats = global_stats(dev.dem_stats(core), ctx, device=core.device)
     ddem = DeviceDEM(band, gny=ctx.gny, gy0=gy0, stats=stats)
+    if len(sizes) > 1 and ("tpi" in what or "std" in what):
+        ddem.share_disc_planes(max(int(s) for s in sizes))  # prefix planes built once for all sizes
     calls = 0
     rx, rx2d = res_x
     ry, ry2d = res_y
@@ -146,6 +148,7 @@ def sweep(core, ctx, sizes, sigmas, res_x, res_y, what=("tpi", "std", "gradient"
             calls += 1
             if sink:
                 sink("std", i, out)
+    ddem.release_disc_planes()
     if "gradient" in what:
         for i, sigma in enumerate(sigmas):
             if sigma <= 1:

@@ -1035,7 +1035,7 @@ __global__ void __launch_bounds__(256) disc_finish_kernel(const DiscParams p) {
 struct DiscPlan {
     DiscParams p;
     int mode, acc;
-    bool fused, hybrid, tiny;
+    bool fused, hybrid, tiny, cached;
     size_t smem;
     int prefix_rows;  // two-pass
     int nchunks;      // hybrid: column-scan chunks
@@ -1067,7 +1067,7 @@ static int max_rb(int mode) { return (mode == TPI_Q || mode == TPI_I) ? 8 : 4; }
 static int narr_of(int mode) { return (mode == TPI_Q || mode == TPI_I) ? 1 : (mode == STD_F ? 3 : 2); }
 
 // Geometry that does not depend on the data range (used by the workspace query too).
-static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPlan& pl) {
+static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPlan& pl, int plane_halo = 0) {
     DiscParams& p = pl.p;
     p.nx = v->nx, p.gny = v->gny, p.in_gy0 = v->in_gy0, p.in_rows = v->in_rows;
     p.out_gy0 = v->out_gy0, p.out_rows = v->out_rows;
@@ -1093,8 +1093,13 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
             return 0;
         }
     }
-    // two-pass: one plane per launch, the workspace is reused by the planes
+    // two-pass: one plane per launch, the workspace is reused by the planes.  With a plane cache the planes are
+    // laid out for the halo of the largest disc that will use them (the kernels only need halo >= size / 2).
     pl.fused = false;
+    if (plane_halo > p.halo) {
+        p.halo = plane_halo;
+        p.haloL = (p.halo + 7) & ~7;
+    }
     const int W = p.haloL + p.nx + p.halo;
     p.pitch = ((W + 7) & ~7) + 8;
     p.prow0 = p.out_gy0 - p.halo;
@@ -1112,6 +1117,9 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
         p.asq = (int)floor((double)p.mid / sqrt(2.0));
         while (2ll * p.asq * p.asq > (long long)p.mid * p.mid) --p.asq;
         while (2ll * (p.asq + 1) * (p.asq + 1) <= (long long)p.mid * p.mid) ++p.asq;
+    }
+    // a cached plane region always has the full (hybrid) layout, whatever the size that happens to use it
+    if (pl.hybrid || plane_halo > 0) {
         pl.nchunks = ceil_div(rows, kColChunk);
         p.cplane_stride = (int64_t)(rows + 1) * p.pitch;
         p.sat_stride = (int64_t)(rows + 1) * p.pitch;
@@ -1153,7 +1161,8 @@ static int ilog2_floor(double x) {
 constexpr double kU32 = 4294967295.0;
 
 // Fill the data-dependent constants.  what: 0 = TPI, 1 = STD.
-static int plan_disc(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, DiscPlan& pl) {
+static int plan_disc(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, DiscPlan& pl,
+                     int cache_size = 0) {
     TOPO_CHECK(size >= 2 && size <= kMaxSize, "kernel size %d outside [2, %d]", size, kMaxSize);
     TOPO_CHECK(isfinite(zmin) && isfinite(zmax) && zmin <= zmax, "DEM range is not finite");
     const double n = (double)disc_count(size);
@@ -1210,7 +1219,11 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
     for (int a = 0; a < narr_of(mode); ++a)
         if (n * vmax[a] < kU32) acc |= 1 << a;
     pl.mode = mode;
-    if (plan_geometry(v, size, narr_of(mode), max_rb(mode), pl)) return -1;
+    // only the size-independent planes (trunc(z) - tmin and its centred square) can be shared between sizes
+    const int plane_halo = (cache_size >= size && (mode == TPI_I || mode == STD_I)) ? cache_size / 2 : 0;
+    pl.cached = plane_halo > 0;
+    if (plan_geometry(v, size, narr_of(mode), max_rb(mode), pl, plane_halo)) return -1;
+    if (pl.fused) pl.cached = false;
     pl.tiny = false;
     if (pl.fused) {
         // instantiated accumulator layouts of the fused kernels: none, plane 0 only, all planes
@@ -1322,22 +1335,38 @@ static int launch_tiny_m(const DiscPlan& pl, cudaStream_t s) {
 // One plane of the two-pass path: prefix planes (+ column prefix and summed-area table for the hybrid walk),
 // then the gather kernel.  PM: plane mode; FIN: descriptor mode finished in place, or -1 for raw sums.
 template <int PM, int FIN>
-static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t s) {
-    const DiscParams& p = pl.p;
+static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t s, topo_disc_cache* cache = nullptr) {
+    DiscParams p = pl.p;
+    bool need_rows = true, need_cols = pl.hybrid;
+    if (cache) {
+        // plane kind 0 = trunc(z) - tmin, 1 = its centred square: one region each, same internal layout as the workspace
+        const int kind = PM == PL_Q ? 1 : 0;
+        unsigned char* region = reinterpret_cast<unsigned char*>(cache->mem) + (size_t)kind * pl.off_partial;
+        p.planes = reinterpret_cast<uint32_t*>(region);
+        p.cplanes = reinterpret_cast<uint32_t*>(region + pl.off_cp);
+        p.sat = reinterpret_cast<unsigned long long*>(region + pl.off_sat);
+        const int row_bit = 1 << (2 * kind), col_bit = 2 << (2 * kind);
+        need_rows = !(cache->valid & row_bit);
+        need_cols = pl.hybrid && !(cache->valid & col_bit);
+        cache->valid |= row_bit | (pl.hybrid ? col_bit : 0);
+    }
     const int warps = kThreads / 32;
-    TOPO_LAUNCH(kernel_label("disc_prefix", PM, 0), s,
-                disc_prefix_kernel<PM><<<ceil_div(pl.prefix_rows, warps), kThreads, 0, s>>>(p, pl.prefix_rows));
+    if (need_rows)
+        TOPO_LAUNCH(kernel_label("disc_prefix", PM, 0), s,
+                    disc_prefix_kernel<PM><<<ceil_div(pl.prefix_rows, warps), kThreads, 0, s>>>(p, pl.prefix_rows));
     const int grid = p.tiles_x * p.tiles_y;
     const size_t smem = pl.smem + span_extra_smem();
     if (pl.hybrid) {
-        unsigned char* ws = reinterpret_cast<unsigned char*>(p.planes);
-        uint32_t* tot_q = reinterpret_cast<uint32_t*>(ws + pl.off_totq);
-        unsigned long long* tot_r = reinterpret_cast<unsigned long long*>(ws + pl.off_totr);
-        dim3 cgrid(ceil_div(p.pitch / 4, 256), pl.nchunks);
-        TOPO_LAUNCH("disc_colsum", s, disc_colsum_kernel<PM><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
-        TOPO_LAUNCH("disc_chunkscan", s,
-                    disc_chunkscan_kernel<<<ceil_div(p.pitch, 256), 256, 0, s>>>(tot_q, tot_r, pl.nchunks, p.pitch, 1));
-        TOPO_LAUNCH("disc_colapply", s, disc_colapply_kernel<PM><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
+        if (need_cols) {
+            unsigned char* ws = reinterpret_cast<unsigned char*>(p.planes);
+            uint32_t* tot_q = reinterpret_cast<uint32_t*>(ws + pl.off_totq);
+            unsigned long long* tot_r = reinterpret_cast<unsigned long long*>(ws + pl.off_totr);
+            dim3 cgrid(ceil_div(p.pitch / 4, 256), pl.nchunks);
+            TOPO_LAUNCH("disc_colsum", s, disc_colsum_kernel<PM><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
+            TOPO_LAUNCH("disc_chunkscan", s,
+                        disc_chunkscan_kernel<<<ceil_div(p.pitch, 256), 256, 0, s>>>(tot_q, tot_r, pl.nchunks, p.pitch, 1));
+            TOPO_LAUNCH("disc_colapply", s, disc_colapply_kernel<PM><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
+        }
         if (acc32)
             TOPO_LAUNCH(kernel_label("disc_hybrid", PM, 1), s, disc_span_kernel<true, true, FIN><<<grid, kThreads, smem, s>>>(p, plane));
         else
@@ -1352,14 +1381,14 @@ static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t 
 }
 
 // tsum_op: 0 = no sharing, 1 = compute the T plane and keep its raw sums in p.tsum, 2 = reuse p.tsum
-static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s) {
+static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo_disc_cache* cache) {
     const bool a0 = pl.acc & 1, a1 = (pl.acc >> 1) & 1, a2 = (pl.acc >> 2) & 1;
     const bool reuse = tsum_op == 2;
     int rc = 0;
     switch (pl.mode) {
         case TPI_Q: return launch_plane<TPI_Q, TPI_Q>(pl, 0, a0, s);
         case TPI_I:
-            if (!reuse) return launch_plane<PL_T, TPI_I>(pl, 0, a0, s);
+            if (!reuse) return launch_plane<PL_T, TPI_I>(pl, 0, a0, s, cache);
             TOPO_LAUNCH("disc_finish<TPI_I>", s, disc_finish_kernel<TPI_I><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
         case TPI_X:
@@ -1368,8 +1397,8 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s) {
             TOPO_LAUNCH("disc_finish<TPI_X>", s, disc_finish_kernel<TPI_X><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
         case STD_I:
-            if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s))) return rc;
-            if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s))) return rc;
+            if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s, cache))) return rc;
+            if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s, cache))) return rc;
             TOPO_LAUNCH("disc_finish<STD_I>", s, disc_finish_kernel<STD_I><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
         default:
@@ -1382,8 +1411,8 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s) {
 }
 
 static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,
-                    int what, int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op, void* ws,
-                    size_t ws_bytes, void* stream) {
+                    int what, int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op,
+                    topo_disc_cache* cache, void* ws, size_t ws_bytes, void* stream) {
     TOPO_CHECK(dem && out, "null pointer");
     if (validate_view(v)) return -1;
     TOPO_CHECK(ld_in >= v->nx && ld_out >= v->nx, "row pitch smaller than nx");
@@ -1393,13 +1422,22 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
         return topo_fill_f32(out, v->out_rows, v->nx, ld_out, NAN, stream);
     }
     DiscPlan pl;
-    if (plan_disc(v, size, what, all_integer, zmin, zmax, pl)) return -1;
+    if (cache && !cache->mem) cache = nullptr;
+    if (plan_disc(v, size, what, all_integer, zmin, zmax, pl, cache ? cache->max_size : 0)) return -1;
+    if (!pl.cached) cache = nullptr;
     if (check_band(v, pl.p.halo)) return -1;
     pl.p.dem = dem, pl.p.out = out, pl.p.ld_in = ld_in, pl.p.ld_out = ld_out;
     cudaStream_t s = (cudaStream_t)stream;
     if (!pl.fused) {
-        TOPO_CHECK(ws != nullptr && ws_bytes >= pl.ws_bytes, "workspace too small: need %zu bytes, got %zu",
-                   pl.ws_bytes, ws_bytes);
+        // with a plane cache the workspace only holds the raw sums of the multi-plane modes
+        const size_t ws_need = cache ? pl.ws_bytes - pl.off_partial : pl.ws_bytes;
+        TOPO_CHECK(ws_need == 0 || (ws != nullptr && ws_bytes >= ws_need), "workspace too small: need %zu bytes, got %zu",
+                   ws_need, ws_bytes);
+        if (cache) {
+            TOPO_CHECK(cache->bytes >= 2 * pl.off_partial, "plane cache too small: need %zu bytes, got %zu",
+                       2 * pl.off_partial, cache->bytes);
+            TOPO_CHECK((reinterpret_cast<uintptr_t>(cache->mem) & 255) == 0, "plane cache must be 256-byte aligned");
+        }
         TOPO_CHECK((reinterpret_cast<uintptr_t>(ws) & 31) == 0, "workspace must be 32-byte aligned");
         TOPO_CHECK((long long)pl.p.tiles_x * pl.p.tiles_y < 2147483647ll, "too many tiles");
         TOPO_CHECK((long long)pl.p.plane_stride + pl.p.pitch < 2147483647ll && (long long)pl.p.cplane_stride + pl.p.pitch < 2147483647ll,
@@ -1409,14 +1447,14 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
             pl.p.cplanes = reinterpret_cast<uint32_t*>((unsigned char*)ws + pl.off_cp);
             pl.p.sat = reinterpret_cast<unsigned long long*>((unsigned char*)ws + pl.off_sat);
         }
-        pl.p.partial = reinterpret_cast<unsigned long long*>((unsigned char*)ws + pl.off_partial);
+        pl.p.partial = reinterpret_cast<unsigned long long*>((unsigned char*)ws + (cache ? 0 : pl.off_partial));
         pl.p.dbg_skip = getenv("TOPO_DBG_SKIP") ? atoi(getenv("TOPO_DBG_SKIP")) : 0;
         if (tsum_op != 0) {
             TOPO_CHECK(tsum != nullptr, "tsum_op %d needs a T-plane sum buffer", tsum_op);
             TOPO_CHECK(pl.mode != TPI_Q, "this size/DEM does not use the T plane (see topo_disc_shares_tsum)");
             pl.p.tsum = tsum;
         }
-        return launch_two_pass(pl, tsum_op, s);
+        return launch_two_pass(pl, tsum_op, s, cache);
     }
     TOPO_CHECK(tsum_op == 0, "T-plane sums are only shared on the two-pass path (see topo_disc_shares_tsum)");
     if (pl.tiny) {
@@ -1469,16 +1507,26 @@ int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer) {
     return (!a.fused && !b.fused) ? 1 : 0;
 }
 
+size_t topo_disc_cache_bytes(const topo_view* v, int max_size) {
+    if (!v || max_size < 2 || max_size > kMaxSize) return 0;
+    DiscPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    plan_geometry(v, max_size, 1, 8, pl, max_size / 2);
+    return pl.fused ? 0 : 2 * pl.off_partial;
+}
+
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,
-                 int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op, void* ws,
-                 size_t ws_bytes, void* stream) {
-    return run_disc(dem, ld_in, out, ld_out, v, size, 0, all_integer, zmin, zmax, tsum, tsum_op, ws, ws_bytes, stream);
+                 int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op,
+                 topo_disc_cache* cache, void* ws, size_t ws_bytes, void* stream) {
+    return run_disc(dem, ld_in, out, ld_out, v, size, 0, all_integer, zmin, zmax, tsum, tsum_op, cache, ws, ws_bytes,
+                    stream);
 }
 
 int topo_std_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,
-                 int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op, void* ws,
-                 size_t ws_bytes, void* stream) {
-    return run_disc(dem, ld_in, out, ld_out, v, size, 1, all_integer, zmin, zmax, tsum, tsum_op, ws, ws_bytes, stream);
+                 int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op,
+                 topo_disc_cache* cache, void* ws, size_t ws_bytes, void* stream) {
+    return run_disc(dem, ld_in, out, ld_out, v, size, 1, all_integer, zmin, zmax, tsum, tsum_op, cache, ws, ws_bytes,
+                    stream);
 }
 
 }  // extern "C"

@@ -72,6 +72,16 @@ class DeviceDEM:
 
     is_device_dem = True  # lets the Dataset container keep it as the values of the DEM variable
 
+    def share_disc_planes(self, max_size):
+        """Announce tpi / std calls at several sizes up to ``max_size`` on this band: the size-independent prefix
+        planes are then built once and kept (7 B/px x 2 planes of HBM at most) until ``release_disc_planes``."""
+        self._plane_hint = int(max_size)
+        return self
+
+    def release_disc_planes(self):
+        self._plane_hint = 0
+        self._plane_cache = None
+
     @property
     def shape(self):
         return (self.rows, self.nx)
@@ -261,9 +271,34 @@ def _disc(name, what, dem, size, out_gy0, out_rows, out, share):
     ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), what)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
     tsum, op = _tsum_plan(dem, v, size, st, share)
+    cache = _plane_cache(dem, v, size, st)
     _lib.call(name, _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
-              1 if st["nonint"] == 0 else 0, st["min"], st["max"], _ptr(tsum), op, _ptr(ws), ws_bytes, _stream())
+              1 if st["nonint"] == 0 else 0, st["min"], st["max"], _ptr(tsum), op,
+              ctypes.byref(cache) if cache is not None else None, _ptr(ws), ws_bytes, _stream())
     return out
+
+
+def _plane_cache(dem, v, size, st):
+    """The ``topo_disc_cache`` of this band, if the caller announced a multi-scale sweep with
+    ``dem.share_disc_planes(max_size)``: integer-valued DEMs build their size-independent prefix planes once."""
+    hint = getattr(dem, "_plane_hint", 0)
+    if not hint or size > hint or st["nonint"] != 0:
+        return None
+    key = (v.in_gy0, v.in_rows, v.out_gy0, v.out_rows, hint)
+    held = getattr(dem, "_plane_cache", None)
+    if held is not None and held[0] == key:
+        return held[1]
+    halo = hint // 2  # the band must cover the halo of the largest disc
+    if v.in_gy0 > max(0, v.out_gy0 - halo) or v.in_gy0 + v.in_rows < min(v.gny, v.out_gy0 + v.out_rows + halo):
+        return None
+    nbytes = _lib.load().topo_disc_cache_bytes(ctypes.byref(v), int(hint))
+    if nbytes == 0:
+        return None
+    mem = _torch().empty(nbytes + 256, dtype=_torch().uint8, device=dem.tensor.device)
+    base = (mem.data_ptr() + 255) & ~255
+    cache = _lib.DiscCache(ctypes.c_void_p(base), nbytes, int(hint), 0)
+    dem._plane_cache = (key, cache, mem)  # `mem` keeps the allocation alive
+    return cache
 
 
 def tpi(dem, size, out_gy0=None, out_rows=None, out=None, share=True):

@@ -118,6 +118,7 @@ def compute_tpi(dem_ds, scales, smth_factors=None, ind_nans=[], crop=None, outdi
     scales_pxl, _ = hlp.scale_to_pixel(scales, dem_ds)
     sigmas = hlp.get_sigmas(smth_factors, scales_pxl)
     ddem, nans = _resident(dem_ds, ind_nans)
+    _share_planes(ddem, scales_pxl, sigmas)
 
     for idx, scale_pxl in enumerate(scales_pxl):
         logger.info(f"Computing scale {scales[idx]} meters with smoothing factor {smth_factors[idx]} ...")
@@ -168,6 +169,7 @@ def compute_std(dem_ds, scales, smth_factors=None, ind_nans=[], crop=None, outdi
     scales_pxl, _ = hlp.scale_to_pixel(scales, dem_ds)
     sigmas = hlp.get_sigmas(smth_factors, scales_pxl)
     ddem, nans = _resident(dem_ds, ind_nans)
+    _share_planes(ddem, scales_pxl, sigmas)
 
     for idx, scale_pxl in enumerate(scales_pxl):
         logger.info(f"Computing scale {scales[idx]} meters with smoothing factor {smth_factors[idx]} ...")
@@ -446,6 +448,12 @@ def _sx_name(radius, azimuth):
 # ---------------------------------------------------------------------------------------------
 # shared by the compute_* drivers: DEM residency and the output stage
 # ---------------------------------------------------------------------------------------------
+def _share_planes(ddem, scales_pxl, sigmas):
+    """Several unsmoothed scales of one DEM: the disc prefix planes do not depend on the scale, build them once."""
+    if len(scales_pxl) > 1 and all(sg is None for sg in sigmas):
+        ddem.share_disc_planes(int(max(scales_pxl)))
+
+
 def _resident(dem_ds, ind_nans):
     """Upload the DEM once for all scales; upload the NaN re-stamp indices once (topo.py:129,139)."""
     import torch
