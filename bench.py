@@ -41,9 +41,7 @@ def make_dem_rows(ny, nx, r0, r1, seed=2):
     """Rows [r0, r1) of the deterministic integer-valued (SRTM-like) synthetic DEM."""
     from topo_descriptors_b200.synth import tiled_fractal_dem
 
-    # the generator is cheap relative to the benchmark; generate whole rows range only
-    z = tiled_fractal_dem(ny, nx, seed=seed, tile=2048, integer=True)
-    return np.ascontiguousarray(z[r0:r1])
+    return tiled_fractal_dem(ny, nx, seed=seed, tile=2048, integer=True, rows=(r0, r1))
 
 
 # ---------------------------------------------------------------------------------------------

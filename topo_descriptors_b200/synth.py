@@ -31,18 +31,19 @@ def fractal_dem(ny, nx, seed=0, zmin=200.0, zmax=3400.0, beta=1.7, integer=False
     return np.ascontiguousarray(z.astype(dtype))
 
 
-def tiled_fractal_dem(ny, nx, seed=0, tile=2048, **kw):
+def tiled_fractal_dem(ny, nx, seed=0, tile=2048, rows=None, **kw):
     """Large DEMs without a large FFT: a ``tile`` x ``tile`` fractal patch mirrored/tiled to
     (ny, nx) plus a smooth large-scale trend.  Deterministic, cheap, keeps realistic local relief;
     used only where the full spectral synthesis would take minutes of host time (16384^2 and up).
+    ``rows=(r0, r1)`` returns only those rows of the (ny, nx) DEM (what one rank of a row-band job needs).
     """
+    r0, r1 = (0, ny) if rows is None else (int(rows[0]), int(rows[1]))
     base = fractal_dem(tile, tile, seed=seed, **kw).astype(np.float32)
     sym = np.concatenate([base, base[:, ::-1]], axis=1)
     sym = np.concatenate([sym, sym[::-1, :]], axis=0)  # 2*tile periodic, continuous
-    ry = -(-ny // sym.shape[0])
     rx = -(-nx // sym.shape[1])
-    z = np.tile(sym, (ry, rx))[:ny, :nx]
-    yy = np.linspace(0.0, 1.0, ny, dtype=np.float32)[:, None]
+    z = np.tile(sym[np.arange(r0, r1) % sym.shape[0]], (1, rx))[:, :nx]
+    yy = np.linspace(0.0, 1.0, ny, dtype=np.float32)[r0:r1, None]
     xx = np.linspace(0.0, 1.0, nx, dtype=np.float32)[None, :]
     z = z + np.float32(150.0) * np.sin(np.float32(2 * np.pi) * yy) * np.cos(np.float32(2 * np.pi) * xx)
     if kw.get("integer"):
