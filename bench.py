@@ -200,6 +200,7 @@ def run_gpu(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_bound = bands.bind_to_gpu_numa(local_rank) if world > 1 else False
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
@@ -353,7 +354,8 @@ def run_gpu(args, rank, world, local_rank):
         "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 in/out; u32 fixed-point + i64 sums (tpi/std), f64 accumulate (gaussian)", "data": "synthetic",
-        "config": workload_config(ny, nx, sizes, extra={"parallelism": f"row bands x{world}, halo exchange over NVLink"}),
+        "config": workload_config(ny, nx, sizes, extra={"parallelism": f"row bands x{world}, halo exchange over NVLink",
+                                                            "numa_bound": bool(numa_bound)}),
         "clocks": clocks.summary(),
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(ctx.rows * nx * 4),
                 "d2h_bytes_per_step": int(d2h[0] // e2e_steps), "steps": e2e_steps,

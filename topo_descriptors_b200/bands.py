@@ -220,6 +220,27 @@ def azimuth_share(azimuths, ctx):
     return list(azimuths)[ctx.rank :: ctx.world]
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU ``index`` (one process per GPU): pinned
+    host buffers are then first-touched on the GPU's own NUMA node, so that the 8 ranks of a box do not push
+    their results through one socket.  Returns True when the affinity was set (best effort, never raises)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = None
+        try:  # NVML ignores CUDA_VISIBLE_DEVICES: go through the UUID of the CUDA device when torch exposes it
+            import torch
+
+            handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(int(index)).uuid))
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:  # no NVML, no permission, or a single-socket host: nothing to do
+        return False
+
+
 def numpy_partition_check(gny, world):
     """Small self-check used by the tests: the partition tiles [0, gny) without gaps."""
     parts = partition_rows(gny, world)
