@@ -22,6 +22,8 @@ if os.environ.get("PROF_FLOAT"):
     core = core + 0.25
 d = DeviceDEM(core)
 _ = d.stats
+if os.environ.get("PROF_SHARE"):  # multi-scale sweep mode: plane cache + octagon walk
+    d.share_disc_planes(int(os.environ["PROF_SHARE"]))
 rx = torch.full((n,), RES_M, dtype=torch.float64, device="cuda")
 ry = torch.full((n,), -RES_M, dtype=torch.float64, device="cuda")
 

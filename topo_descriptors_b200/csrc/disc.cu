@@ -26,6 +26,8 @@
 //              through L1/L2 with LDG.64 (measured 29.9 words/clk/SM vs 19.5 for LDG.32).  CTAs are
 //              rasterised in 16-tile-wide super-columns so that the rows in flight stay L2-resident.
 #include <math.h>
+
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 
@@ -70,7 +72,13 @@ struct DiscParams {
     uint32_t* cplanes;  // hybrid: column-prefix planes (2 copies per plane), prefix_rows + 1 rows each
     unsigned long long* sat;  // hybrid: summed-area planes (64-bit), prefix_rows + 1 rows each
     int64_t cplane_stride, sat_stride;  // elements between consecutive copies / planes
-    int asq;     // hybrid: half-side of the square inscribed in the disc, floor(mid / sqrt(2))
+    int asq;     // hybrid: half-side of the square inscribed in the disc, floor(mid / sqrt(2)); octagon: u
+    // octagon decomposition (plane cache only): O = {|i| <= u, |j| <= u, |i| + |j| <= u + v}, v = isqrt(mid^2 - u^2)
+    int oct;         // 1 = the diagonal tables below exist and the walk uses the octagon
+    int oct_v;       // v
+    int oct_ndiag;   // corner diagonals |i| + |j| = u + v + 1 .. u + v + ndiag
+    uint32_t* eplanes;           // diagonal prefix of the plane values: E1 A, E1 B, E2 A, E2 B (plane_stride apart)
+    unsigned long long* dplanes; // diagonal sums of the 64-bit row prefix: D1, D2 (sat_stride apart)
     int dbg_skip;  // profiling only (TOPO_DBG_SKIP): 1 = skip column caps, 2 = skip row caps, 4 = skip square
     unsigned long long* partial;  // two-pass, multi-plane modes: raw disc sums, [plane][out_rows][nx]
     int64_t partial_stride;
@@ -797,6 +805,102 @@ __global__ void __launch_bounds__(256) disc_colapply_kernel(const DiscParams p, 
     }
 }
 
+// ---- octagon tables: running sums along the diagonals --------------------------------------------------------
+//   DIR = +1 (blockIdx.z = 0): T[r][c] = v[r][c] + T[r-1][c-1]      (c - r constant)
+//   DIR = -1 (blockIdx.z = 1): T[r][c] = v[r][c] + T[r-1][c+1]      (c + r constant)
+// One thread per (diagonal, chunk of kDiagChunk rows); lanes = neighbouring diagonals => at every row the warp
+// touches consecutive columns (coalesced).  Three phases like the column scan: chunk totals -> exclusive scan of the
+// totals along each diagonal -> running sums offset by the scanned totals.  Sums that start outside the plane start
+// at 0: every lookup is a difference of two entries of the same diagonal, so that cancels.
+// WIDE = false: v = plane value (uint32 wrap-around, two shifted copies)  -> E1 / E2  (corner diagonals of the disc)
+// WIDE = true : v = 64-bit row prefix (rows 1.. of p.sat, BEFORE the column scan turns it into the summed-area table)
+//               -> D1 / D2 (sheared summed-area tables: a 45-degree trapezoid costs 4 lookups)
+constexpr int kDiagChunk = 256;
+
+template <int MODE>
+__device__ __forceinline__ uint32_t plane_value_at(const DiscParams& p, int r, int c) {
+    const int gy = p.prow0 + r, gx = c - p.haloL;
+    float z = 0.f;  // zero padding outside the image (rows outside the band are never used, see load4_zero)
+    if (gy >= 0 && gy < p.gny && gy >= p.in_gy0 && gy < p.in_gy0 + p.in_rows && gx >= 0 && gx < p.nx)
+        z = __ldg(p.dem + (int64_t)(gy - p.in_gy0) * p.ld_in + gx);
+    uint32_t q[ModeTraits<MODE>::NARR];
+    convert<MODE>(p, z, q);
+    return q[0];
+}
+
+// PHASE 0: chunk totals -> tot[dir][chunk][t];  PHASE 1: running sums, starting from the scanned totals
+template <int MODE, bool WIDE, int PHASE>
+__global__ void __launch_bounds__(256) disc_diag_kernel(const DiscParams p, unsigned long long* __restrict__ tot, int ndiag) {
+    const int W = p.haloL + p.nx + p.halo;
+    const int wc = WIDE ? W + 1 : W;  // columns of the source
+    const int dir = blockIdx.z ? -1 : 1;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= p.nrows + wc - 1) return;
+    // column at row 0: c0 = t - (nrows - 1) for DIR +1 (then c = c0 + r), c0 = t for DIR -1 (then c = c0 - r)
+    const int c0 = dir > 0 ? t - (p.nrows - 1) : t;
+    const int r_begin = max(dir > 0 ? max(0, -c0) : max(0, c0 - (wc - 1)), (int)blockIdx.y * kDiagChunk);
+    const int r_end = min(dir > 0 ? min(p.nrows, wc - c0) : min(p.nrows, c0 + 1), ((int)blockIdx.y + 1) * kDiagChunk);
+    unsigned long long* slot = tot + ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * ndiag + t;
+    unsigned long long acc = PHASE == 1 ? *slot : 0ull;
+    auto source = [&](int r) -> unsigned long long {
+        const int c = c0 + dir * r;
+        if constexpr (WIDE) return __ldg(p.sat + (int64_t)(r + 1) * p.pitch + c);
+        else return plane_value_at<MODE>(p, r, c);
+    };
+    auto store = [&](int r, unsigned long long v) {
+        const int c = c0 + dir * r;
+        if constexpr (WIDE) {
+            (p.dplanes + (blockIdx.z ? p.sat_stride : 0))[(int64_t)r * p.pitch + c] = v;
+        } else {
+            uint32_t* dstA = p.eplanes + (blockIdx.z ? 2 * p.plane_stride : 0) + (int64_t)r * p.pitch;
+            dstA[c] = (uint32_t)v;
+            if (c > 0) dstA[p.plane_stride + c - 1] = (uint32_t)v;  // shifted copy: B[c] = A[c + 1]
+        }
+    };
+    int r = r_begin;
+    for (; r + 8 <= r_end; r += 8) {
+        unsigned long long v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = source(r + k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            acc += v[k];
+            if (PHASE == 1) store(r + k, acc);
+        }
+    }
+    for (; r < r_end; ++r) {
+        acc += source(r);
+        if (PHASE == 1) store(r, acc);
+    }
+    if (PHASE == 0) *slot = acc;
+}
+
+// exclusive scan of the chunk totals along every diagonal (both directions)
+__global__ void __launch_bounds__(256) disc_diag_chunkscan_kernel(unsigned long long* __restrict__ tot, int nchunks, int ndiag) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= ndiag) return;
+    unsigned long long* col = tot + (int64_t)blockIdx.y * nchunks * ndiag + t;
+    unsigned long long run = 0ull;
+    for (int c = 0; c < nchunks; ++c) {
+        const unsigned long long v = col[(int64_t)c * ndiag];
+        col[(int64_t)c * ndiag] = run;
+        run += v;
+    }
+}
+
+// corner diagonals of the octagon: for d = u + v + 1 + n the lattice points (|i|, |j|) = (q, d - q) inside the disc
+// and inside |i|, |j| <= u form the run q = lo .. hi; dtab[n] = lo | hi << 16 (hi < lo: empty)
+__device__ __forceinline__ void build_diag_table(const DiscParams& p, int* dtab) {
+    const int u = p.asq, s = p.asq + p.oct_v, m2 = p.mid * p.mid;
+    for (int n = threadIdx.x; n < p.oct_ndiag; n += blockDim.x) {
+        const int d = s + 1 + n;
+        int lo = max(0, d - u), hi = min(u, d);
+        while (lo <= hi && lo * lo + (d - lo) * (d - lo) > m2) ++lo;
+        while (hi >= lo && hi * hi + (d - hi) * (d - hi) > m2) --hi;
+        dtab[n] = (hi < lo) ? (1 | (0 << 16)) : (lo | (hi << 16));
+    }
+}
+
 // ---- two-pass span kernels: ONE plane per launch, 8 rows x 2 adjacent pixels per thread -----------------------
 // All lookups are aligned 64-bit pairs (P[j], P[j+1]) from the A/B copies.  Accumulators are 32-bit when the
 // whole disc sum of the plane fits (ACC32), else 64-bit.
@@ -881,21 +985,87 @@ __device__ __forceinline__ void row_walk_grouped(const DiscParams& p, const int*
 }
 
 // Hybrid: inscribed square from the 64-bit summed-area table + row caps (grouped walk) + column caps.
+// Octagon variant (p.oct, plane cache only): the O(1) part is the octagon |i| <= u, |j| <= u, |i| + |j| <= u + v
+// (rectangle from the summed-area table + two 45-degree trapezoids from the sheared tables D1 / D2), the caps
+// shrink to |i| > u and |j| > u, and the four corner slivers are walked along their diagonals with the diagonal
+// prefix tables E1 / E2: 4 (mid - u) + 4 ndiag lines instead of 4 (mid - a) -- 284 vs 472 at size 801.
+// (profiles/proto/octagon.py is the CPU prototype that pins the index conventions.)
 template <bool ACC32>
-__device__ __forceinline__ void hybrid_walk(const DiscParams& p, const int* __restrict__ tab, int prow, int lcx, int lead,
-                                            int lag, PairAcc& A) {
+__device__ __forceinline__ void hybrid_walk(const DiscParams& p, const int* __restrict__ tab, const int* __restrict__ dtab,
+                                            int prow, int lcx, int lead, int lag, PairAcc& A) {
     const int a_sq = p.asq, mid = p.mid, pitch = p.pitch;
-    // ---- square: rows [py-a, py+a], columns [lcx-a, lcx+a] (+1 for the second pixel)
+    const int rv = p.oct ? p.oct_v : a_sq;  // half-height of the summed-area rectangle (its half-width is a_sq = u)
+    // ---- rectangle: rows [py-rv, py+rv], columns [lcx-a, lcx+a] (+1 for the second pixel)
 #pragma unroll
     for (int b = 0; b < kRB; ++b) {
-        const unsigned long long* top = p.sat + (int64_t)(prow + b - a_sq) * pitch + lcx;      // S row py-a
-        const unsigned long long* bot = p.sat + (int64_t)(prow + b + a_sq + 1) * pitch + lcx;  // S row py+a+1
+        const unsigned long long* top = p.sat + (int64_t)(prow + b - rv) * pitch + lcx;      // S row py-rv
+        const unsigned long long* bot = p.sat + (int64_t)(prow + b + rv + 1) * pitch + lcx;  // S row py+rv+1
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const unsigned long long v = __ldg(bot + q + a_sq + 1) - __ldg(top + q + a_sq + 1) - __ldg(bot + q - a_sq) +
                                          __ldg(top + q - a_sq);
             A.s32[b][q] = (uint32_t)v;
             A.s64[b][q] = v;
+        }
+    }
+    if (p.oct) {
+        const int u = a_sq, v = p.oct_v, s = u + v;
+        const unsigned long long* D1 = p.dplanes;
+        const unsigned long long* D2 = p.dplanes + p.sat_stride;
+        if (u > v) {
+            // top trapezoid: rows i = -u .. -v-1, columns x - (s+i) .. x + (s+i); bottom: rows v+1 .. u, half-width s - i
+#pragma unroll
+            for (int b = 0; b < kRB; ++b) {
+                const int64_t y = prow + b;
+                const unsigned long long* t1 = D1 + (y - v - 1) * pitch + lcx;  // row y + i1      (i1 = -v-1)
+                const unsigned long long* t0 = D1 + (y - u - 1) * pitch + lcx;  // row y + i0 - 1  (i0 = -u)
+                const unsigned long long* s1 = D2 + (y - v - 1) * pitch + lcx;
+                const unsigned long long* s0 = D2 + (y - u - 1) * pitch + lcx;
+                const unsigned long long* b1 = D2 + (y + u) * pitch + lcx;      // row y + j1      (j1 = u)
+                const unsigned long long* b0 = D2 + (y + v) * pitch + lcx;      // row y + j0 - 1  (j0 = v+1)
+                const unsigned long long* c1 = D1 + (y + u) * pitch + lcx;
+                const unsigned long long* c0 = D1 + (y + v) * pitch + lcx;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const unsigned long long top = (__ldg(t1 + q + s - v) - __ldg(t0 + q + s - u)) -
+                                                   (__ldg(s1 + q - s + v + 1) - __ldg(s0 + q - s + u + 1));
+                    const unsigned long long bot = (__ldg(b1 + q + s - u + 1) - __ldg(b0 + q + s - v + 1)) -
+                                                   (__ldg(c1 + q - s + u) - __ldg(c0 + q - s + v));
+                    A.s32[b][q] += (uint32_t)(top + bot);
+                    A.s64[b][q] += top + bot;
+                }
+            }
+        }
+        // corner slivers: diagonal |i| + |j| = d, run q = lo .. hi of |i| in every quadrant.  Quadrant by quadrant:
+        // neighbouring diagonals end on neighbouring rows / columns, so their lookups reuse the same L1 lines.
+        const int estride = (int)p.plane_stride;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t* tbl = p.eplanes + (k < 2 ? 2 * p.plane_stride : 0);  // quadrants 0, 1: E2; 2, 3: E1
+#pragma unroll 1
+            for (int n = 0; n < p.oct_ndiag; ++n) {
+                const int e = dtab[n];
+                const int lo = e & 0xffff, hi = e >> 16;
+                if (hi < lo) continue;
+                const int d = s + 1 + n;
+                // (row, column) offsets of the far / near end of the run, see octagon.py
+                int rh, rl, ch, cl;
+                if (k == 0) rh = hi, rl = lo - 1, ch = d - hi, cl = d - lo + 1;
+                else if (k == 1) rh = -lo, rl = -hi - 1, ch = -d + lo, cl = -d + hi + 1;
+                else if (k == 2) rh = hi, rl = lo - 1, ch = -d + hi, cl = -d + lo - 1;
+                else rh = -lo, rl = -hi - 1, ch = d - lo, cl = d - hi - 1;
+                const uint32_t oh = (uint32_t)(lcx + ((ch & 1) ? (estride + ch - 1) : ch));
+                const uint32_t ol = (uint32_t)(lcx + ((cl & 1) ? (estride + cl - 1) : cl));
+                const uint32_t* ph = opaque_ptr(tbl + (int64_t)(prow + rh) * pitch);
+                const uint32_t* pl = opaque_ptr(tbl + (int64_t)(prow + rl) * pitch);
+#pragma unroll
+                for (int b = 0; b < kRB; ++b) {
+                    const uint2 hv = __ldg(reinterpret_cast<const uint2*>(ph + oh));
+                    const uint2 lv = __ldg(reinterpret_cast<const uint2*>(pl + ol));
+                    pair_add<ACC32>(A, b, hv, lv);
+                    ph += pitch, pl += pitch;
+                }
+            }
         }
     }
     // ---- top / bottom caps: kernel rows |i - mid| > a
@@ -935,10 +1105,12 @@ __device__ __forceinline__ void hybrid_walk(const DiscParams& p, const int* __re
 
 // FIN: TPI_Q / TPI_I = finish in place (single-plane descriptors); -1 = store the raw sums of plane `plane`.
 template <bool ACC32, bool HYBRID, int FIN>
-__global__ void __launch_bounds__(kThreads) disc_span_kernel(const DiscParams p, int plane) {
+__global__ void __launch_bounds__(kThreads, HYBRID ? 3 : 1) disc_span_kernel(const DiscParams p, int plane) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     int* tab = reinterpret_cast<int*>(smem_raw);
+    int* dtab = tab + ((p.k + 7) & ~7);  // corner diagonals of the octagon (hybrid walk with a plane cache)
     build_span_table(p, tab);
+    if (HYBRID && p.oct) build_diag_table(p, dtab);
     __syncthreads();
 
     // super-column raster: tiles of kSuperCols columns are walked top to bottom before moving right
@@ -980,7 +1152,7 @@ __global__ void __launch_bounds__(kThreads) disc_span_kernel(const DiscParams p,
     // slower on B200 (the walk is bound by L1 wavefronts, not by L2 traffic, and lockstep adds 24 steps): off.
     const int lead = 0, lag = 0;
     if constexpr (HYBRID)
-        hybrid_walk<ACC32>(p, tab, prow, lcx, lead, lag, A);
+        hybrid_walk<ACC32>(p, tab, dtab, prow, lcx, lead, lag, A);
     else
         row_walk_grouped<ACC32>(p, tab, prow + p.c, lcx, 0, p.k, lead, lag, A);
 
@@ -1040,7 +1212,8 @@ struct DiscPlan {
     int prefix_rows;  // two-pass
     int nchunks;      // hybrid: column-scan chunks
     // workspace layout (byte offsets)
-    size_t off_cp, off_sat, off_totq, off_totr, off_partial;
+    size_t off_cp, off_sat, off_totq, off_totr, off_e, off_d, off_dtot, off_partial;
+    int ndchunks, ndiag_threads;  // octagon tables: row chunks and diagonals of the diagonal scans
     size_t ws_bytes;
 };
 
@@ -1131,6 +1304,42 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
         bytes = align(pl.off_totq + (size_t)pl.nchunks * p.pitch * 4);
         pl.off_totr = bytes;
         bytes = align(pl.off_totr + (size_t)pl.nchunks * p.pitch * 8);
+    }
+    // octagon tables (plane cache only: they are worth building when several sizes share them)
+    p.oct = 0;
+    if (plane_halo > 0) {
+        pl.off_e = bytes;
+        bytes = align(pl.off_e + (size_t)p.plane_stride * 4 * 4);  // E1 A/B, E2 A/B
+        pl.off_d = bytes;
+        bytes = align(pl.off_d + (size_t)p.sat_stride * 8 * 2);    // D1, D2
+        pl.ndchunks = ceil_div(rows, kDiagChunk);
+        pl.ndiag_threads = rows + p.pitch;
+        pl.off_dtot = bytes;
+        bytes = align(pl.off_dtot + (size_t)2 * pl.ndchunks * pl.ndiag_threads * 8);  // chunk totals of the diagonal scans
+        if (pl.hybrid && !getenv("TOPO_NO_OCTAGON")) {
+            // u minimising the walked lines 4 (mid - u) + 4 (dmax - u - v), v = isqrt(mid^2 - u^2) <= u
+            const long long m = p.mid, m2 = m * m;
+            auto isqrt = [](long long n) {
+                long long r = (long long)floor(sqrt((double)n));
+                while (r * r > n) --r;
+                while ((r + 1) * (r + 1) <= n) ++r;
+                return r;
+            };
+            long long dmax = 0;
+            for (long long q = 0; q <= m; ++q) dmax = std::max(dmax, q + isqrt(m2 - q * q));
+            long long best = -1, bu = 0, bv = 0;
+            for (long long u = (long long)floor((double)m / sqrt(2.0)); u <= m; ++u) {
+                const long long v = isqrt(m2 - u * u);
+                if (v > u) continue;
+                const long long lines = 4 * (m - u) + 4 * (dmax - (u + v));
+                if (best < 0 || lines < best) best = lines, bu = u, bv = v;
+            }
+            p.oct = 1;
+            p.asq = (int)bu;
+            p.oct_v = (int)bv;
+            p.oct_ndiag = (int)(dmax - (bu + bv));
+            pl.smem += (size_t)((p.oct_ndiag + 7) & ~7) * 4;
+        }
     }
     pl.off_partial = bytes;
     if (narr > 1) {
@@ -1345,6 +1554,8 @@ static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t 
         p.planes = reinterpret_cast<uint32_t*>(region);
         p.cplanes = reinterpret_cast<uint32_t*>(region + pl.off_cp);
         p.sat = reinterpret_cast<unsigned long long*>(region + pl.off_sat);
+        p.eplanes = reinterpret_cast<uint32_t*>(region + pl.off_e);
+        p.dplanes = reinterpret_cast<unsigned long long*>(region + pl.off_d);
         const int row_bit = 1 << (2 * kind), col_bit = 2 << (2 * kind);
         need_rows = !(cache->valid & row_bit);
         need_cols = pl.hybrid && !(cache->valid & col_bit);
@@ -1362,6 +1573,18 @@ static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t 
             uint32_t* tot_q = reinterpret_cast<uint32_t*>(ws + pl.off_totq);
             unsigned long long* tot_r = reinterpret_cast<unsigned long long*>(ws + pl.off_totr);
             dim3 cgrid(ceil_div(p.pitch / 4, 256), pl.nchunks);
+            if (cache) {
+                // octagon tables: D1 / D2 from the 64-bit row prefix (still in the summed-area buffer), E1 / E2 from the DEM
+                unsigned long long* dtot = reinterpret_cast<unsigned long long*>(ws + pl.off_dtot);
+                const int nd = pl.ndiag_threads;
+                dim3 dgrid(ceil_div(nd, 256), pl.ndchunks, 2), sgrid(ceil_div(nd, 256), 2);
+                TOPO_LAUNCH("disc_diag64_totals", s, (disc_diag_kernel<PM, true, 0><<<dgrid, 256, 0, s>>>(p, dtot, nd)));
+                TOPO_LAUNCH("disc_diag_chunkscan", s, disc_diag_chunkscan_kernel<<<sgrid, 256, 0, s>>>(dtot, pl.ndchunks, nd));
+                TOPO_LAUNCH("disc_diag64_apply", s, (disc_diag_kernel<PM, true, 1><<<dgrid, 256, 0, s>>>(p, dtot, nd)));
+                TOPO_LAUNCH("disc_diag32_totals", s, (disc_diag_kernel<PM, false, 0><<<dgrid, 256, 0, s>>>(p, dtot, nd)));
+                TOPO_LAUNCH("disc_diag_chunkscan", s, disc_diag_chunkscan_kernel<<<sgrid, 256, 0, s>>>(dtot, pl.ndchunks, nd));
+                TOPO_LAUNCH("disc_diag32_apply", s, (disc_diag_kernel<PM, false, 1><<<dgrid, 256, 0, s>>>(p, dtot, nd)));
+            }
             TOPO_LAUNCH("disc_colsum", s, disc_colsum_kernel<PM><<<cgrid, 256, 0, s>>>(p, tot_q, tot_r, pl.nchunks));
             TOPO_LAUNCH("disc_chunkscan", s,
                         disc_chunkscan_kernel<<<ceil_div(p.pitch, 256), 256, 0, s>>>(tot_q, tot_r, pl.nchunks, p.pitch, 1));
