@@ -112,11 +112,12 @@ int topo_nan_indices_f32(const float* dem, int64_t ld_in, int rows, int nx, int 
  * value is integral (SRTM-like DEMs: exact one-plane TPI, two-plane STD).
  * Small sizes run fused (tile + halo prefix in shared memory); larger sizes run two passes through
  * `ws` (prefix planes in HBM, gathered with 64-bit loads). */
-size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi, 1 std*/);
+size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi, 1 std*/,
+                                 int cache_max_size /* max_size of the topo_disc_cache that will be passed, else 0 */);
 /* tpi(size) and std(size) of an integer-valued DEM both need the disc sums of trunc(z): when this returns 1
  * the first call can keep them (tsum_op = 1, tsum = out_rows*nx uint64 on the DEVICE) and the second reuse
  * them (tsum_op = 2), which removes one of the three gather passes of a tpi+std pair.  tsum_op = 0: off. */
-int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer);
+int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, int cache_max_size /* 0: no plane cache */);
 size_t topo_disc_cache_bytes(const topo_view* v, int max_size);
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
                  int size, int all_integer, double zmin, double zmax, unsigned long long* tsum,

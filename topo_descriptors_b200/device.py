@@ -239,14 +239,14 @@ def _nan_result(v, like, n=1):
     return outs
 
 
-def _tsum_plan(dem, v, size, st, share):
+def _tsum_plan(dem, v, size, st, share, cache_size=0):
     """T-plane sum sharing between tpi(size) and std(size) of the same integer-valued DEM band:
     returns (tensor or None, op) with op 0 = off, 1 = compute + keep, 2 = reuse."""
     torch = _torch()
     if not share or st["nonint"] != 0:
         return None, 0
     L = _lib.load()
-    if not L.topo_disc_shares_tsum(ctypes.byref(v), int(size), 1):
+    if not L.topo_disc_shares_tsum(ctypes.byref(v), int(size), 1, int(cache_size)):
         return None, 0
     key = (int(size), v.out_gy0, v.out_rows)
     cached = getattr(dem, "_tsum", None)
@@ -268,10 +268,10 @@ def _disc(name, what, dem, size, out_gy0, out_rows, out, share):
         fill(out, float("nan"))
         return out
     L = _lib.load()
-    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), what)
-    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
-    tsum, op = _tsum_plan(dem, v, size, st, share)
     cache = _plane_cache(dem, v, size, st)
+    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), what, cache.max_size if cache is not None else 0)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
+    tsum, op = _tsum_plan(dem, v, size, st, share, cache.max_size if cache is not None else 0)
     _lib.call(name, _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
               1 if st["nonint"] == 0 else 0, st["min"], st["max"], _ptr(tsum), op,
               ctypes.byref(cache) if cache is not None else None, _ptr(ws), ws_bytes, _stream())
