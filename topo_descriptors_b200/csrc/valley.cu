@@ -6,20 +6,25 @@
 // lives in registers for all 180 angles; norm is clipped at 0 on the way out.  Zero padding outside
 // the global image, scipy 'same' centring through the per-angle anchors.
 //
-// Register blocking: a thread owns 4 vertically adjacent pixels in each of 2 columns 32 apart (lanes = columns,
+// Register blocking: a thread owns 4 vertically adjacent pixels in each of 4 columns 32 apart (lanes = columns,
 // so the shared-memory DEM reads are conflict-free) and walks a kernel column top to bottom: each step loads one
 // weight vector (warp-uniform 128-bit load served by L1) and one DEM sample per column and issues
-// 2 x 4 x n_ch FMAs (24 for the usual 3 flats) with a rotating window of 4 weight vectors -- ~85% of the issue
-// slots are FFMA.  The DEM tile + halo is staged once per CTA and reused by all angles.
+// 4 x 4 x n_ch FMAs (48 for the usual 3 flats) with a rotating window of 4 weight vectors -- ~90% of the issue
+// slots are FFMA (128 registers, 2 CTAs per SM; 2 columns per thread measured 13% slower on B200).
+// The DEM tile + halo is staged once per CTA and reused by all angles.
 #include <math.h>
 
 #include "common.cuh"
 
+#ifndef TOPO_VALLEY_VC
+#define TOPO_VALLEY_VC 4
+#endif
+
 namespace topo {
 
 constexpr int kVQ = 4;            // pixels per thread and column (vertical)
-constexpr int kVC = 2;            // columns per thread, 32 apart
-constexpr int kVTileX = 32 * kVC; // block (32, 8): 64 columns x 8 thread rows x 4 pixels
+constexpr int kVC = TOPO_VALLEY_VC;  // columns per thread, 32 apart
+constexpr int kVTileX = 32 * kVC; // block (32, 8): 128 columns x 8 thread rows x 4 pixels
 constexpr int kVTileY = 8 * kVQ;  // 32 output rows per CTA
 
 struct ValleyParams {
