@@ -248,6 +248,38 @@ def test_library_exports_every_declared_symbol():
     assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, 0) == 0 and lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, 801) == 1
 
 
+def test_c_abi_argument_errors_are_reported_before_any_launch():
+    """Every entry point validates its arguments first: bad calls return an error code and a message through
+    topo_last_error() without touching the GPU (so this runs on a CPU-only box)."""
+    import ctypes
+
+    fake = ctypes.c_void_p(0x1000)  # never dereferenced: the checks fail first
+    null = ctypes.c_void_p(0)
+    v = _lib.View(64, 48, 0, 48, 0, 48)
+    vp = ctypes.byref(v)
+
+    def fails(name, *args, match):
+        with pytest.raises(_lib.TopoError, match=match or None):
+            _lib.call(name, *args)
+
+    fails("topo_tpi_f32", null, 64, fake, 64, vp, 5, 0, 0.0, 1.0, null, 0, None, null, 0, null, match="null pointer")
+    fails("topo_tpi_f32", fake, 64, fake, 64, vp, 9000, 0, 0.0, 1.0, null, 0, None, null, 0, null, match="kernel size")
+    fails("topo_std_f32", fake, 64, fake, 64, vp, 5, 0, float("nan"), 1.0, null, 0, None, null, 0, null, match="not finite")
+    fails("topo_std_f32", fake, 32, fake, 64, vp, 5, 0, 0.0, 1.0, null, 0, None, null, 0, null, match="pitch")
+    bad = _lib.View(64, 48, 10, 20, 0, 48)  # the band does not contain the requested rows
+    fails("topo_tpi_f32", fake, 64, fake, 64, ctypes.byref(bad), 5, 0, 0.0, 1.0, null, 0, None, null, 0, null, match="")
+    fails("topo_tpi_f32", fake, 64, fake, 64, vp, 301, 1, 0.0, 100.0, null, 0, None, null, 0, null, match="workspace too small")
+    fails("topo_sx_f32", fake, 64, fake, 64, 64 * 48, vp, fake, fake, fake, 0, 3, ctypes.c_float(10.0), -3, 3, -3, 3, null,
+          match="n_az")
+    fails("topo_sx_f32", fake, 64, fake, 64, 64 * 48, vp, fake, fake, fake, 1, 3, ctypes.c_float(10.0), -4, 3, -3, 3, null,
+          match="exceed the window")
+    fails("topo_valley_ridge_f32", fake, 64, fake, fake, 64, vp, fake, fake, fake, fake, 180, 5, 9, 9, null,
+          match="flat_list of length 5")
+    fails("topo_fill_na_f32", fake, 64, fake, 64, 48, 200000, null, 0, ctypes.c_float(0.0), null, null, match="")
+    # size 1: kernel sum - 1 == 0 in the reference; handled by the fill entry point, which needs a real buffer -> not called here
+    assert _lib.load().topo_last_error()
+
+
 def test_no_cpu_fallback():
     import torch
 
