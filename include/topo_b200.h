@@ -41,17 +41,19 @@ typedef struct topo_view {
 } topo_view;
 
 /* Prefix planes shared by the tpi / std calls of ONE DEM band at several sizes (a multi-scale sweep): the
- * planes of trunc(z) - tmin and of its centred square do not depend on the disc size, so they are built by the
- * first call that needs them and reused by the later ones (integer-valued DEMs, two-pass sizes).
- * The caller owns `mem` (DEVICE, 256-byte aligned, >= topo_disc_cache_bytes(v, max_size)), starts with
- * valid = 0 and passes the same struct, DEM, view and range to every call; the input band must cover the halo
- * of max_size.  NULL (or mem = NULL) = no sharing. */
+ * planes (trunc(z) - tmin, its centred square, and for float DEMs the fraction / the quantised elevation with
+ * the fixed-point scale of max_size) do not depend on the disc size, so they are built by the first call that
+ * needs them and reused by the later ones -- together with the column-prefix, summed-area and diagonal tables
+ * of the octagon walk.  The caller owns `mem` (DEVICE, 256-byte aligned,
+ * >= topo_disc_cache_bytes(v, max_size, all_integer)), starts with valid = 0 and passes the same struct, DEM,
+ * view, all_integer flag and range to every call; the input band must cover the halo of max_size.
+ * NULL (or mem = NULL) = no sharing. */
 typedef struct topo_disc_cache {
     void* mem;
     size_t bytes;
     int max_size; /* the planes are laid out for discs up to this size */
-    int valid;    /* in/out: bit 0 / 1 = row prefix / column prefix + summed-area table of trunc(z) - tmin,
-                     bit 2 / 3 = the same for the squares plane */
+    int valid;    /* in/out: bits 2k / 2k+1 = row prefix / column-side tables of plane kind k
+                     (0 trunc(z) - tmin, 1 its square, 2 fraction, 3 quantised elevation) */
 } topo_disc_cache;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -118,7 +120,7 @@ size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi,
  * the first call can keep them (tsum_op = 1, tsum = out_rows*nx uint64 on the DEVICE) and the second reuse
  * them (tsum_op = 2), which removes one of the three gather passes of a tpi+std pair.  tsum_op = 0: off. */
 int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, int cache_max_size /* 0: no plane cache */);
-size_t topo_disc_cache_bytes(const topo_view* v, int max_size);
+size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer);
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
                  int size, int all_integer, double zmin, double zmax, unsigned long long* tsum,
                  int tsum_op, topo_disc_cache* cache, void* ws, size_t ws_bytes, void* stream);

@@ -206,10 +206,18 @@ def test_disc_plane_cache_is_transparent():
     for s in (201, 151, 301):
         assert bool((dev.std(band, s, lo, hi - lo) == want[s][1][lo:hi]).all()), s
         assert bool((dev.tpi(band, s, lo, hi - lo) == want[s][0][lo:hi]).all()), s
-    # float DEMs do not use the cache (their planes depend on the size): still correct
-    z = fractal_dem(300, 340, seed=16)
-    f = DeviceDEM(dev.to_device(z)).share_disc_planes(201)
-    assert maxdiff(dev.tpi(f, 201).cpu().numpy(), O.tpi_exact(z, 201)) <= TOL_M and getattr(f, "_plane_cache", None) is None
+    # float DEMs share planes too, with the fixed-point scales of the largest size: within tolerance at every size
+    z = fractal_dem(420, 460, seed=16)
+    f = DeviceDEM(dev.to_device(z)).share_disc_planes(301)
+    for s in (301, 41, 151, 88, 9):
+        assert maxdiff(dev.tpi(f, s).cpu().numpy(), O.tpi_exact(z, s)) <= TOL_M, s
+        assert maxdiff(dev.std(f, s).cpu().numpy(), O.std_exact(z, s)) <= TOL_M, s
+    assert f._plane_cache is not None and f._plane_cache[1].valid != 0
+    # a range so wide that the quantised plane is too coarse: exact two-plane TPI (T + fraction planes), shared as well
+    zw = fractal_dem(300, 340, seed=17, zmin=-2.0e5, zmax=3.0e6)
+    g = DeviceDEM(dev.to_device(zw)).share_disc_planes(151)
+    for s in (151, 61):
+        assert maxdiff(dev.tpi(g, s).cpu().numpy(), O.tpi_exact(zw, s)) <= 0.26, s  # float32 resolution of 3e6 is 0.25
 
 
 def test_std_sigma(golden):

@@ -243,7 +243,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 17, 0, 0) == 0  # fused: no workspace
     assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 801, 0, 0) > 4 * 900 * 1440
     # with a plane cache the planes live there: the workspace shrinks and mid sizes walk the cached planes
-    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801) > 10 * 4 * 900 * 1440
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1) > 10 * 4 * 900 * 1440
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0) == 2 * lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1)
     assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 41, 1, 801) >= 2 * 8 * 900 * 1440  # raw sums of two planes
     assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, 0) == 0 and lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, 801) == 1
 

@@ -1375,12 +1375,14 @@ static int ilog2_floor(double x) {
 constexpr double kU32 = 4294967295.0;
 
 // Fill the data-dependent constants.  what: 0 = TPI, 1 = STD.
-static int plan_disc(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, DiscPlan& pl,
-                     int cache_size = 0) {
+// span_size: the disc size the fixed-point scales are laid out for -- `size` itself, or the largest size of a sweep
+// that shares its planes through a topo_disc_cache (then every size of the sweep sees the same planes).
+static int plan_disc_impl(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, DiscPlan& pl,
+                          int cache_size, int span_size) {
     TOPO_CHECK(size >= 2 && size <= kMaxSize, "kernel size %d outside [2, %d]", size, kMaxSize);
     TOPO_CHECK(isfinite(zmin) && isfinite(zmax) && zmin <= zmax, "DEM range is not finite");
     const double n = (double)disc_count(size);
-    const double span = (double)size;  // longest run of a kernel row
+    const double span = (double)span_size;  // longest run of a kernel row
     // integer-part range, including the zero padding value
     const double tlo = fmin(0.0, trunc(zmin)), thi = fmax(0.0, trunc(zmax));
     const double trange = thi - tlo;
@@ -1396,7 +1398,7 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
         // a slightly coarser scale lets the whole disc sum live in 32 bits (one IADD3 per row)
         int S32 = ilog2_floor(kU32 / (n * range));
         if (S32 > 20) S32 = 20;
-        if (S32 >= 13) S = S32;
+        if (S32 >= 13 && span_size == size) S = S32;  // (depends on the size: not for shared planes)
         if (S >= 10) {
             mode = TPI_Q;
             p.scale = (float)ldexp(1.0, S);
@@ -1433,8 +1435,8 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
     for (int a = 0; a < narr_of(mode); ++a)
         if (n * vmax[a] < kU32) acc |= 1 << a;
     pl.mode = mode;
-    // only the size-independent planes (trunc(z) - tmin and its centred square) can be shared between sizes
-    const int plane_halo = (cache_size >= size && (mode == TPI_I || mode == STD_I)) ? cache_size / 2 : 0;
+    // shared planes: laid out for the halo of the largest size of the sweep
+    const int plane_halo = cache_size >= size ? cache_size / 2 : 0;
     pl.cached = plane_halo > 0;
     if (plan_geometry(v, size, narr_of(mode), max_rb(mode), pl, plane_halo)) return -1;
     if (pl.fused) pl.cached = false;
@@ -1457,6 +1459,17 @@ static int plan_disc(const topo_view* v, int size, int what, int all_integer, do
     p.nc0_scaled = n * (double)p.c0i * p.inv_scale;
     p.n_tmin = n * (double)p.tmin;
     return 0;
+}
+
+// Fill the data-dependent constants.  what: 0 = TPI, 1 = STD.  With a plane cache the plan is first made for shared
+// planes (scales of the largest size); a size that runs fused anyway, or whose shared layout does not fit the 32-bit
+// span sums, gets its own plan.
+static int plan_disc(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, DiscPlan& pl,
+                     int cache_size = 0) {
+    if (cache_size >= size && size >= 2) {
+        if (plan_disc_impl(v, size, what, all_integer, zmin, zmax, pl, cache_size, cache_size) == 0 && !pl.fused) return 0;
+    }
+    return plan_disc_impl(v, size, what, all_integer, zmin, zmax, pl, 0, size);
 }
 
 static const char* mode_name(int mode) {
@@ -1553,8 +1566,11 @@ static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t 
     DiscParams p = pl.p;
     bool need_rows = true, need_cols = pl.hybrid;
     if (cache) {
-        // plane kind 0 = trunc(z) - tmin, 1 = its centred square: one region each, same internal layout as the workspace
-        const int kind = PM == PL_Q ? 1 : 0;
+        // plane kind 0 = trunc(z) - tmin, 1 = its centred square, 2 = fraction, 3 = quantised elevation (float DEMs):
+        // one region each, same internal layout as the workspace
+        const int kind = PM == PL_Q ? 1 : PM == PL_F ? 2 : PM == TPI_Q ? 3 : 0;
+        TOPO_CHECK(cache->bytes >= (size_t)(kind + 1) * pl.off_partial, "plane cache too small: need %zu bytes, got %zu",
+                   (size_t)(kind + 1) * pl.off_partial, cache->bytes);
         unsigned char* region = reinterpret_cast<unsigned char*>(cache->mem) + (size_t)kind * pl.off_partial;
         p.planes = reinterpret_cast<uint32_t*>(region);
         p.cplanes = reinterpret_cast<uint32_t*>(region + pl.off_cp);
@@ -1614,14 +1630,14 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo
     const bool reuse = tsum_op == 2;
     int rc = 0;
     switch (pl.mode) {
-        case TPI_Q: return launch_plane<TPI_Q, TPI_Q>(pl, 0, a0, s);
+        case TPI_Q: return launch_plane<TPI_Q, TPI_Q>(pl, 0, a0, s, cache);
         case TPI_I:
             if (!reuse) return launch_plane<PL_T, TPI_I>(pl, 0, a0, s, cache);
             TOPO_LAUNCH("disc_finish<TPI_I>", s, disc_finish_kernel<TPI_I><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
         case TPI_X:
-            if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s))) return rc;
-            if ((rc = launch_plane<PL_F, -1>(pl, 1, a1, s))) return rc;
+            if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s, cache))) return rc;
+            if ((rc = launch_plane<PL_F, -1>(pl, 1, a1, s, cache))) return rc;
             TOPO_LAUNCH("disc_finish<TPI_X>", s, disc_finish_kernel<TPI_X><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
         case STD_I:
@@ -1630,9 +1646,9 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo
             TOPO_LAUNCH("disc_finish<STD_I>", s, disc_finish_kernel<STD_I><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
         default:
-            if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s))) return rc;
-            if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s))) return rc;
-            if ((rc = launch_plane<PL_F, -1>(pl, 2, a2, s))) return rc;
+            if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s, cache))) return rc;
+            if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s, cache))) return rc;
+            if ((rc = launch_plane<PL_F, -1>(pl, 2, a2, s, cache))) return rc;
             TOPO_LAUNCH("disc_finish<STD_F>", s, disc_finish_kernel<STD_F><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
     }
@@ -1662,8 +1678,6 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
         TOPO_CHECK(ws_need == 0 || (ws != nullptr && ws_bytes >= ws_need), "workspace too small: need %zu bytes, got %zu",
                    ws_need, ws_bytes);
         if (cache) {
-            TOPO_CHECK(cache->bytes >= 2 * pl.off_partial, "plane cache too small: need %zu bytes, got %zu",
-                       2 * pl.off_partial, cache->bytes);
             TOPO_CHECK((reinterpret_cast<uintptr_t>(cache->mem) & 255) == 0, "plane cache must be 256-byte aligned");
         }
         TOPO_CHECK((reinterpret_cast<uintptr_t>(ws) & 31) == 0, "workspace must be 32-byte aligned");
@@ -1717,7 +1731,7 @@ size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what, int cac
     const int modes_tpi[3] = {TPI_Q, TPI_X, TPI_I}, modes_std[3] = {STD_I, STD_F, STD_F};
     for (int m = 0; m < 3; ++m) {
         const int mode = what == 0 ? modes_tpi[m] : modes_std[m];
-        const bool cached = cache_max_size >= size && (mode == TPI_I || mode == STD_I);
+        const bool cached = cache_max_size >= size;
         DiscPlan pl;
         memset(&pl, 0, sizeof(pl));
         plan_geometry(v, size, narr_of(mode), max_rb(mode), pl, cached ? cache_max_size / 2 : 0);
@@ -1739,12 +1753,14 @@ int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, int cac
     return (!a.fused && !b.fused) ? 1 : 0;
 }
 
-size_t topo_disc_cache_bytes(const topo_view* v, int max_size) {
+size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer) {
     if (!v || max_size < 2 || max_size > kMaxSize) return 0;
     DiscPlan pl;
     memset(&pl, 0, sizeof(pl));
     plan_geometry(v, max_size, 1, 8, pl, max_size / 2);
-    return pl.fused ? 0 : 2 * pl.off_partial;
+    // integer-valued DEMs use two plane kinds (trunc(z) - tmin, its square); float DEMs add the fraction and the
+    // quantised-elevation planes
+    return pl.fused ? 0 : (size_t)(all_integer ? 2 : 4) * pl.off_partial;
 }
 
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,

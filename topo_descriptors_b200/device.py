@@ -280,9 +280,9 @@ def _disc(name, what, dem, size, out_gy0, out_rows, out, share):
 
 def _plane_cache(dem, v, size, st):
     """The ``topo_disc_cache`` of this band, if the caller announced a multi-scale sweep with
-    ``dem.share_disc_planes(max_size)``: integer-valued DEMs build their size-independent prefix planes once."""
+    ``dem.share_disc_planes(max_size)``: the size-independent prefix planes are then built once per sweep."""
     hint = getattr(dem, "_plane_hint", 0)
-    if not hint or size > hint or st["nonint"] != 0:
+    if not hint or size > hint:
         return None
     key = (v.in_gy0, v.in_rows, v.out_gy0, v.out_rows, hint)
     held = getattr(dem, "_plane_cache", None)
@@ -291,7 +291,7 @@ def _plane_cache(dem, v, size, st):
     halo = hint // 2  # the band must cover the halo of the largest disc
     if v.in_gy0 > max(0, v.out_gy0 - halo) or v.in_gy0 + v.in_rows < min(v.gny, v.out_gy0 + v.out_rows + halo):
         return None
-    nbytes = _lib.load().topo_disc_cache_bytes(ctypes.byref(v), int(hint))
+    nbytes = _lib.load().topo_disc_cache_bytes(ctypes.byref(v), int(hint), 1 if st["nonint"] == 0 else 0)
     if nbytes == 0:
         return None
     mem = _torch().empty(nbytes + 256, dtype=_torch().uint8, device=dem.tensor.device)
