@@ -38,11 +38,16 @@ def main():
         ry = (torch.full((ny,), -25.0, dtype=torch.float64, device=device), 0)
         got = {}
         bands.sweep(core, ctx, sizes, sigmas, rx, ry, sink=lambda n, i, t: got.__setitem__((n, i), t.clone()))
+        # like with like: the bands run the cached multi-size sweep (shared planes; for float DEMs that means the
+        # fixed-point scale of the largest size), so the whole-image reference runs it too
+        whole.share_disc_planes(max(sizes))
         for i, size in enumerate(sizes):
             ref = {"tpi": dev.tpi(whole, size), "std": dev.std(whole, size)}
             g = DeviceDEM(dev.gauss(whole, sigmas[i], sigmas[i]))
             outs = dev.gradient_from_smooth(g, g, rx[0], 0, ry[0], 0)
             ref.update(dict(zip(("dx", "dy", "slope", "aspect"), outs)))
+            if i == len(sizes) - 1:
+                whole.release_disc_planes()
             for name, r in ref.items():
                 same = torch.equal(got[(name, i)], r[ctx.r0 : ctx.r1])
                 if not same:

@@ -424,6 +424,26 @@ def test_bands_bit_identical():
         assert (dev.gauss(band, sigma, sigma, lo, hi - lo) == ref_g[lo:hi]).all()
 
 
+def test_cached_sweep_on_thin_bands_like_8_gpus():
+    """The partition tests/mgpu_check.py uses at 8 ranks (1500 rows -> bands of ~187 rows, halo 150 of size 301),
+    emulated on one GPU: every band runs the cached multi-size sweep and must equal the whole-image result."""
+    from topo_descriptors_b200 import bands
+
+    ny, nx = 1500, 1111
+    zi = fractal_dem(ny, nx, seed=5, integer=True)
+    whole = DeviceDEM(dev.to_device(zi))
+    sizes = [5, 21, 67, 201, 301]
+    want = {s: (dev.tpi(whole, s, share=False), dev.std(whole, s, share=False)) for s in sizes}
+    halo = bands.sweep_halo(sizes, [])
+    for rank in range(8):
+        ctx = bands.BandContext(ny, nx, rank, 8)
+        band = _band(whole.tensor, ctx.r0, ctx.r1, halo, whole.stats).share_disc_planes(max(sizes))
+        for s in sizes:
+            assert bool((dev.tpi(band, s, ctx.r0, ctx.rows) == want[s][0][ctx.r0 : ctx.r1]).all()), (rank, s)
+            assert bool((dev.std(band, s, ctx.r0, ctx.rows) == want[s][1][ctx.r0 : ctx.r1]).all()), (rank, s)
+        band.release_disc_planes()
+
+
 def test_bands_valley_sx_bit_identical():
     """Row bands of valley_ridge and Sx equal the same rows of the whole-image result."""
     from topo_descriptors_b200 import bands
