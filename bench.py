@@ -322,9 +322,17 @@ def run_gpu(args, rank, world, local_rank):
         return 8  # every other kernel on this path: 4 B in, 4 B out
 
     achieved = alg_bytes_px(dom_name) * band_px / (avg_ms * 1e-3) / 1e9
+    # DRAM bytes per algorithmic byte from the committed `ncu --set full` capture (profiles/r01_ncu_full_summary.csv,
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch on an 8192^2 DEM / its algorithmic bytes)
+    ncu_dram_ratio = {"gauss_axis0": 1.11, "grad_from_smooth": 0.96, "disc_hybrid": 21.0}
+    ratio = next((r for k, r in ncu_dram_ratio.items() if dom_name.startswith(k)), None)
+    traffic = None if ratio is None else int(ratio * alg_bytes_px(dom_name) * band_px)
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+        "frac": round(achieved / peak, 4), "traffic": traffic,
+        "traffic_source": "algorithmic bytes of one launch x the DRAM/algorithmic ratio of the ncu --set full capture in "
+                          "profiles/r01_ncu_full_summary.csv" if traffic is not None else None,
+        "peak_source": peak_src,
         "share_of_step": round(dom_v["ms"] / total_kernel_ms, 3),
         "note": "the kernels that dominate config 4 are the wide-radius ones (float64 Gaussian taps, disc span gathers): "
                 "FP64-pipe / L1-wavefront bound by construction, so their HBM fraction is small; the HBM-bound kernels of "
