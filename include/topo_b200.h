@@ -112,8 +112,11 @@ int topo_nan_indices_f32(const float* dem, int64_t ld_in, int rows, int nx, int 
  *        `dem.astype("int32") ** 2` (topo.py:300): the squares use the truncated elevation.
  * zmin/zmax: GLOBAL finite range of the DEM (from topo_dem_stats_f32); all_integer: 1 if every
  * value is integral (SRTM-like DEMs: exact one-plane TPI, two-plane STD).
- * Small sizes run fused (tile + halo prefix in shared memory); larger sizes run two passes through
- * `ws` (prefix planes in HBM, gathered with 64-bit loads). */
+ * Sizes 5..13 (odd) use register sliding sums, small sizes run fused (tile + halo prefix in shared
+ * memory), larger sizes run two passes through `ws` (prefix planes in HBM, gathered with 64-bit loads;
+ * odd discs as an inscribed square / octagon from summed-area tables + caps).  cache: see
+ * topo_disc_cache above -- with it the planes live in the cache and `ws` only holds raw plane sums;
+ * pass the cache's max_size to the *_workspace_bytes / shares_tsum queries (0 without a cache). */
 size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi, 1 std*/,
                                  int cache_max_size /* max_size of the topo_disc_cache that will be passed, else 0 */);
 /* tpi(size) and std(size) of an integer-valued DEM both need the disc sums of trunc(z): when this returns 1

@@ -18,13 +18,18 @@
 //   STD_I : t - tmin,  (t - cmid)^2                   2 planes, exact (integer-valued DEM)
 //   STD_F : t - tmin,  (t - cmid)^2, (frac+1)*2^Sf    3 planes, exact
 //
-// Two execution shapes, same span walk (a thread owns 2 adjacent pixels x RB rows):
-//   fused    : CTA = 128 x 32 output tile; tile + halo is loaded with 128-bit loads, converted, scanned
-//              with warp shuffles into shared memory; lanes = pixel pairs => conflict-free LDS.
-//   two-pass : prefix planes go to HBM (workspace) in two copies, P and P shifted by one element, so that
-//              the pair (P[j], P[j+1]) is always one aligned 64-bit load; the span walk gathers them
-//              through L1/L2 with LDG.64 (measured 29.9 words/clk/SM vs 19.5 for LDG.32).  CTAs are
-//              rasterised in 16-tile-wide super-columns so that the rows in flight stay L2-resident.
+// Execution shapes (DESIGN.md section 4 has the measurements):
+//   tiny     : odd sizes 5..13, one-plane modes: register sliding sums, no prefix at all.
+//   fused    : CTA = 128 x 32 output tile; tile + halo is loaded with 128-bit loads, converted, scanned with warp
+//              shuffles into shared memory; a thread owns 2 pixels x RB rows; conflict-free LDS.
+//   two-pass : prefix planes go to HBM in two copies, P and P shifted by one element, so that the pair
+//              (P[j], P[j+1]) is always one aligned 64-bit load; the walk gathers them through L1/L2 with LDG.64
+//              (measured 29.9 words/clk/SM vs 19.5 for LDG.32).  CTAs are rasterised in 16-tile-wide super-columns
+//              so that the rows in flight stay L2-resident.  Odd discs use the hybrid decomposition: an O(1) core
+//              (inscribed square, or -- in multi-size sweeps -- an octagon from sheared summed-area tables) + row
+//              caps + column caps (+ corner diagonals from diagonal prefix tables), see hybrid_walk.
+//   plane cache (topo_disc_cache): every plane and table above is independent of the disc size, so a multi-size
+//              sweep builds them once, for the halo of its largest size.
 #include <math.h>
 
 #include <algorithm>
