@@ -80,3 +80,11 @@ def test_single_rank_is_identity():
     assert band is core and gy0 == 0
     st = {"min": 1.0, "max": 2.0, "nonfinite": 0, "nonint": 0, "sum": 3.0, "sumsq": 5.0, "n": 60}
     assert bands.global_stats(st, ctx) == st
+
+
+def test_round_robin_share_and_numa_binding_are_safe_without_gpus():
+    ctx = bands.BandContext(100, 10, 2, 4)
+    assert bands.azimuth_share(range(0, 360, 45), ctx) == [90, 270]
+    assert bands.azimuth_share([], ctx) == []
+    # no NVML device here: best effort, must not raise
+    assert bands.bind_to_gpu_numa(0) in (False, True)
