@@ -4,7 +4,6 @@ world_size 2 and 3 over gloo (the N > 1 path of bench.py / bands.sweep without t
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist

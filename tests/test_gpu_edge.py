@@ -9,7 +9,7 @@ import pytest
 
 from oracle import oracle as O
 from topo_descriptors_b200 import _xr, helpers as hlp, topo
-from topo_descriptors_b200.synth import dem_dataset, fractal_dem
+from topo_descriptors_b200.synth import dem_dataset
 
 pytestmark = pytest.mark.gpu
 
