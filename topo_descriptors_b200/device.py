@@ -278,6 +278,18 @@ def _disc(name, what, dem, size, out_gy0, out_rows, out, share):
     return out
 
 
+def _fits_in_hbm(nbytes, device):
+    """True if ``nbytes`` can still be allocated on ``device`` (free HBM + what torch's allocator holds unused).
+    Fails open: any problem with the query means "yes"."""
+    try:
+        torch = _torch()
+        free, _total = torch.cuda.mem_get_info(device)
+        pooled = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        return int(nbytes) <= int(free) + max(int(pooled), 0)
+    except Exception:
+        return True
+
+
 def _plane_cache(dem, v, size, st):
     """The ``topo_disc_cache`` of this band, if the caller announced a multi-scale sweep with
     ``dem.share_disc_planes(max_size)``: the size-independent prefix planes are then built once per sweep."""
@@ -292,8 +304,8 @@ def _plane_cache(dem, v, size, st):
     if v.in_gy0 > max(0, v.out_gy0 - halo) or v.in_gy0 + v.in_rows < min(v.gny, v.out_gy0 + v.out_rows + halo):
         return None
     nbytes = _lib.load().topo_disc_cache_bytes(ctypes.byref(v), int(hint), 1 if st["nonint"] == 0 else 0)
-    if nbytes == 0:
-        return None
+    if nbytes == 0 or not _fits_in_hbm(2 * nbytes, dem.tensor.device):
+        return None  # (a DEM too large for shared planes runs every size on its own workspace, as without the hint)
     mem = _torch().empty(nbytes + 256, dtype=_torch().uint8, device=dem.tensor.device)
     base = (mem.data_ptr() + 255) & ~255
     cache = _lib.DiscCache(ctypes.c_void_p(base), nbytes, int(hint), 0)
