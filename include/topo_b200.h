@@ -124,6 +124,13 @@ size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi,
  * them (tsum_op = 2), which removes one of the three gather passes of a tpi+std pair.  tsum_op = 0: off. */
 int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, int cache_max_size /* 0: no plane cache */);
 size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer);
+/* Host-only introspection (no launch): the plan topo_tpi_f32 (what = 0) / topo_std_f32 (what = 1) would run.
+ * info[16]: 0 mode (0 TPI_Q, 1 TPI_X, 2 STD_I, 3 STD_F, 4 TPI_I), 1 fused, 2 hybrid, 3 tiny, 4 uses the plane
+ * cache, 5 octagon walk, 6 u (octagon) or a (inscribed square), 7 v, 8 corner diagonals, 9 32-bit accumulator
+ * mask, 10 dynamic shared memory of the walk, 11 plane halo, 12 plane pitch, 13 plane rows, 14 workspace
+ * bytes, 15 bytes of one cached plane region. */
+int topo_disc_plan_info(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax,
+                        int cache_max_size, long long* info);
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
                  int size, int all_integer, double zmin, double zmax, unsigned long long* tsum,
                  int tsum_op, topo_disc_cache* cache, void* ws, size_t ws_bytes, void* stream);

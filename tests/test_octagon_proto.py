@@ -65,3 +65,38 @@ def _cover_count(m):
 def test_octagon_pieces_cover_every_disc_pixel_exactly_once(m):
     cover, disc = _cover_count(m)
     assert np.array_equal(cover, disc.astype(np.int32)), m
+
+
+def test_cxx_planner_matches_the_prototype_for_every_odd_size():
+    """The host planner of csrc/disc.cu (through the host-only topo_disc_plan_info) picks the same octagon as the
+    CPU prototype, for every odd size the cached two-pass walk accepts, and stays inside the hardware limits."""
+    import ctypes
+    import math
+
+    from topo_descriptors_b200 import _lib
+
+    lib = _lib.load()
+    info = (ctypes.c_longlong * 16)()
+    sizes = list(range(41, 1203, 2)) + [2001, 3001, 4095, 8191]
+    for size in sizes:
+        v = _lib.View(2048, 4096, 0, 4096, 0, 4096)
+        assert lib.topo_disc_plan_info(ctypes.byref(v), size, 0, 1, 0.0, 500.0, size, info) == 0, size
+        mode, fused, hybrid, tiny, cached, oct_, u, vv, ndiag, acc, smem = list(info)[:11]
+        assert (mode, fused, hybrid, tiny, cached, oct_) == (4, 0, 1, 0, 1, 1), size
+        m = size // 2
+        pu, pv, ps, _, _ = octagon.plan(m)
+        dmax = max(q + math.isqrt(m * m - q * q) for q in range(m + 1))
+        assert (u, vv, ndiag) == (pu, pv, dmax - ps), size
+        assert vv <= u <= m and u * u + vv * vv <= m * m and (u + 1) ** 2 * 2 > m * m
+        assert smem <= 200 * 1024 and info[11] == m
+    # without a cache: the inscribed square; small sizes: fused / tiny; even sizes: plain row spans
+    v = _lib.View(2048, 4096, 0, 4096, 0, 4096)
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 801, 0, 1, 0.0, 500.0, 0, info) == 0
+    assert (info[2], info[4], info[5], info[6]) == (1, 0, 0, int(400 / math.sqrt(2)))
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 9, 0, 1, 0.0, 500.0, 801, info) == 0 and (info[1], info[3]) == (1, 1)
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 21, 1, 1, 0.0, 500.0, 801, info) == 0 and (info[1], info[3]) == (1, 0)
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 400, 0, 1, 0.0, 500.0, 801, info) == 0 and (info[1], info[2], info[4]) == (0, 0, 1)
+    # float DEM: quantised plane with the scale of the sweep's largest size, or the exact two-plane mode for wide ranges
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 201, 0, 0, 0.0, 3400.5, 801, info) == 0 and info[0] == 0 and info[4] == 1
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 201, 0, 0, -2e5, 3e6, 801, info) == 0 and info[0] == 1
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 201, 1, 0, 0.0, 3400.5, 801, info) == 0 and info[0] == 3

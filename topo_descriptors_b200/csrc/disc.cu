@@ -1758,6 +1758,21 @@ int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, int cac
     return (!a.fused && !b.fused) ? 1 : 0;
 }
 
+int topo_disc_plan_info(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax,
+                        int cache_max_size, long long* info) {
+    // host-only introspection of the plan run_disc would execute (no launch, no GPU needed): used by the CPU tests
+    TOPO_CHECK(info != nullptr, "null pointer");
+    if (validate_view(v)) return -1;
+    DiscPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    if (plan_disc(v, size, what, all_integer, zmin, zmax, pl, cache_max_size)) return -1;
+    info[0] = pl.mode, info[1] = pl.fused, info[2] = pl.hybrid, info[3] = pl.tiny, info[4] = pl.cached;
+    info[5] = pl.p.oct, info[6] = pl.p.asq, info[7] = pl.p.oct_v, info[8] = pl.p.oct_ndiag, info[9] = pl.acc;
+    info[10] = (long long)pl.smem, info[11] = pl.p.halo, info[12] = pl.p.pitch, info[13] = pl.prefix_rows;
+    info[14] = (long long)pl.ws_bytes, info[15] = (long long)pl.off_partial;
+    return 0;
+}
+
 size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer) {
     if (!v || max_size < 2 || max_size > kMaxSize) return 0;
     DiscPlan pl;
