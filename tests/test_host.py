@@ -205,6 +205,16 @@ def test_fill_na_matches_scipy_nearest():
         want_ind, want = O.fill_na_exact(z, x)
         assert np.array_equal(ind[0], want_ind[0]) and np.array_equal(ind[1], want_ind[1])
         assert np.array_equal(hlp.get_da(filled).values, want, equal_nan=True)
+    # non-uniform and unsorted x coordinates (the row-by-row path sorts per row like interp1d)
+    xs = base["x"].values
+    warped = xs + 7.0 * np.sin(np.arange(xs.size))
+    perm = rng.permutation(xs.size)
+    for x, zz in ((warped, z), (xs[perm], z[:, perm])):
+        ds = _xr.Dataset({"alti": (("y", "x"), zz)}, coords={"x": x, "y": base["y"].values}, attrs=base.attrs)
+        ind, filled = hlp.fill_na(ds)
+        want_ind, want = O.fill_na_exact(zz, x)
+        assert np.array_equal(ind[1], want_ind[1])
+        assert np.array_equal(hlp.get_da(filled).values, want, equal_nan=True)
 
 
 def test_to_netcdf_npz_sink(tmp_path):

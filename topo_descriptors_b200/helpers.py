@@ -143,8 +143,44 @@ def fill_na(dem_ds):
     if _xr.have_xarray() and not isinstance(dem_ds, _xr.Dataset):  # pragma: no cover
         return ind_nans, dem_ds.interpolate_na(dim="x", method="nearest", fill_value="extrapolate")
 
-    filled = values.copy()
     x = np.asarray(dem_ds["x"].values, dtype=np.float64)
+    dx = np.diff(x)
+    if len(ind_nans[0]) == 0:
+        filled = values.copy()
+    elif x.size > 1 and (np.all(dx > 0) or np.all(dx < 0)):
+        filled = _fill_nearest_monotonic(values, nan_mask, x)
+    else:
+        filled = _fill_nearest_rows(values, nan_mask, x, ind_nans)
+    name = list(dem_ds)[0]
+    out = _xr.Dataset({name: (da.dims, filled)}, coords=dem_ds.coords, attrs=dem_ds.attrs)
+    return ind_nans, out
+
+
+def _fill_nearest_monotonic(values, nan_mask, x):
+    """Nearest valid cell along x for every missing cell, all rows at once (x strictly monotonic): running
+    last-valid / next-valid indices, the nearer one in x wins, exact half-way points take the lower-x neighbour,
+    rows without a valid cell stay NaN."""
+    ny, nx = values.shape
+    idx = np.arange(nx)
+    left = np.maximum.accumulate(np.where(nan_mask, -1, idx[None, :]), axis=1)
+    right = np.minimum.accumulate(np.where(nan_mask, nx, idx[None, :])[:, ::-1], axis=1)[:, ::-1]
+    rows, cols = np.nonzero(nan_mask)
+    li, ri = left[rows, cols], right[rows, cols]
+    has_l, has_r = li >= 0, ri < nx
+    xl = x[np.clip(li, 0, nx - 1)]
+    xr = x[np.clip(ri, 0, nx - 1)]
+    dl, dr = np.abs(x[cols] - xl), np.abs(xr - x[cols])
+    take_left = has_l & (~has_r | (dl < dr) | ((dl == dr) & (xl < xr)))
+    pick = np.where(take_left, li, ri)
+    ok = has_l | has_r
+    filled = values.copy()
+    filled[rows[ok], cols[ok]] = values[rows[ok], np.clip(pick[ok], 0, nx - 1)]
+    return filled
+
+
+def _fill_nearest_rows(values, nan_mask, x, ind_nans):
+    """Row-by-row variant for unsorted x coordinates (sorted per row like scipy's interp1d does)."""
+    filled = values.copy()
     for row in np.unique(ind_nans[0]):
         good = ~nan_mask[row]
         if not good.any():
@@ -158,9 +194,7 @@ def fill_na(dem_ds):
         mid = (xg[:-1] + xg[1:]) / 2.0
         idx = np.searchsorted(mid, q, side="left")
         filled[row, nan_mask[row]] = vg[idx]
-    name = list(dem_ds)[0]
-    out = _xr.Dataset({name: (da.dims, filled)}, coords=dem_ds.coords, attrs=dem_ds.attrs)
-    return ind_nans, out
+    return filled
 
 
 def get_dem_netcdf(path_dem):
