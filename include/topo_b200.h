@@ -45,7 +45,7 @@ typedef struct topo_view {
  * the fixed-point scale of max_size) do not depend on the disc size, so they are built by the first call that
  * needs them and reused by the later ones -- together with the column-prefix, summed-area and diagonal tables
  * of the octagon walk.  The caller owns `mem` (DEVICE, 256-byte aligned,
- * >= topo_disc_cache_bytes(v, max_size, all_integer)), starts with valid = 0 and passes the same struct, DEM,
+ * >= topo_disc_cache_bytes(v, max_size, all_integer, zmin, zmax)), starts with valid = 0 and passes the same struct, DEM,
  * view, all_integer flag and range to every call; the input band must cover the halo of max_size.
  * NULL (or mem = NULL) = no sharing. */
 typedef struct topo_disc_cache {
@@ -53,7 +53,8 @@ typedef struct topo_disc_cache {
     size_t bytes;
     int max_size; /* the planes are laid out for discs up to this size */
     int valid;    /* in/out: bits 2k / 2k+1 = row prefix / column-side tables of plane kind k
-                     (0 trunc(z) - tmin, 1 its square, 2 fraction, 3 quantised elevation) */
+                     (0 trunc(z) - tmin, 1 its square (or the low 16 bits of a split square), 2 fraction,
+                     3 quantised elevation; the high half of a split square takes the next free kind) */
 } topo_disc_cache;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -67,6 +68,12 @@ long long topo_launch_count(void);
  * launch order) into buf and clears the records. */
 int topo_profile_enable(int on);
 int topo_profile_dump(char* buf, size_t cap);
+/* Execution-shape switches, all on by default: "octagon" (octagon core of the shared-plane disc walk), "tiny"
+ * (register sliding sums for sizes 5..13), "sx_tma" (TMA-staged Sx tile), "gauss_fft" (float64 FFT overlap-save for
+ * wide Gaussian radii), "grad_fused" (single-kernel small-radius gradient).  Every setting gives the same results
+ * through another kernel shape (the tests flip them to compare shapes bit for bit); nothing is read from the
+ * process environment.  Returns 0, or -1 for an unknown name. */
+int topo_set_option(const char* name, int value);
 
 /* ---- DEM statistics (one pass, cached by the host per uploaded DEM) ------------------------ */
 /* out_stats (DEVICE, 8 doubles): [0] min [1] max [2] #non-finite [3] #non-integer-valued
@@ -117,18 +124,25 @@ int topo_nan_indices_f32(const float* dem, int64_t ld_in, int rows, int nx, int 
  * odd discs as an inscribed square / octagon from summed-area tables + caps).  cache: see
  * topo_disc_cache above -- with it the planes live in the cache and `ws` only holds raw plane sums;
  * pass the cache's max_size to the *_workspace_bytes / shares_tsum queries (0 without a cache). */
-size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi, 1 std*/,
+/* The queries take the same all_integer / zmin / zmax / cache size as the call they describe and make the same plan,
+ * so the answer is exactly what the call needs (0 for the fused shapes).  STD on a DEM whose size x range^2 would
+ * overflow the 32-bit span sums of the squares (e.g. a 0..4800 m range from size ~800) splits the square plane in
+ * 16-bit halves: one more gather pass, same exact result. */
+size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi, 1 std*/, int all_integer,
+                                 double zmin, double zmax,
                                  int cache_max_size /* max_size of the topo_disc_cache that will be passed, else 0 */);
 /* tpi(size) and std(size) of an integer-valued DEM both need the disc sums of trunc(z): when this returns 1
  * the first call can keep them (tsum_op = 1, tsum = out_rows*nx uint64 on the DEVICE) and the second reuse
  * them (tsum_op = 2), which removes one of the three gather passes of a tpi+std pair.  tsum_op = 0: off. */
-int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, int cache_max_size /* 0: no plane cache */);
-size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer);
+int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, double zmin, double zmax,
+                          int cache_max_size /* 0: no plane cache */);
+/* 0: this DEM / size cannot share planes (the calls then run un-cached; pass cache = NULL). */
+size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer, double zmin, double zmax);
 /* Host-only introspection (no launch): the plan topo_tpi_f32 (what = 0) / topo_std_f32 (what = 1) would run.
- * info[16]: 0 mode (0 TPI_Q, 1 TPI_X, 2 STD_I, 3 STD_F, 4 TPI_I), 1 fused, 2 hybrid, 3 tiny, 4 uses the plane
+ * info[17]: 0 mode (0 TPI_Q, 1 TPI_X, 2 STD_I, 3 STD_F, 4 TPI_I), 1 fused, 2 hybrid, 3 tiny, 4 uses the plane
  * cache, 5 octagon walk, 6 u (octagon) or a (inscribed square), 7 v, 8 corner diagonals, 9 32-bit accumulator
  * mask, 10 dynamic shared memory of the walk, 11 plane halo, 12 plane pitch, 13 plane rows, 14 workspace
- * bytes, 15 bytes of one cached plane region. */
+ * bytes, 15 bytes of one cached plane region, 16 split square planes. */
 int topo_disc_plan_info(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax,
                         int cache_max_size, long long* info);
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,

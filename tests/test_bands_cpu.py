@@ -7,6 +7,7 @@ import socket
 import pytest
 import torch
 import torch.distributed as dist
+import numpy as np
 import torch.multiprocessing as mp
 
 from topo_descriptors_b200 import bands
@@ -16,7 +17,10 @@ def test_partition_rows():
     assert bands.partition_rows(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert bands.partition_rows(16384, 8)[3] == (6144, 8192)
     for gny, w in [(1, 1), (7, 2), (900, 8), (16384, 8), (5, 5)]:
-        p = bands.numpy_partition_check(gny, w)
+        parts = bands.partition_rows(gny, w)
+        assert parts[0][0] == 0 and parts[-1][1] == gny
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        p = np.array(parts)
         sizes = p[:, 1] - p[:, 0]
         assert sizes.max() - sizes.min() <= 1
     ctx = bands.BandContext(100, 8, rank=1, world=4)

@@ -191,15 +191,15 @@ def test_disc_plane_cache_is_transparent():
     assert shared._plane_cache is not None and shared._plane_cache[1].valid == 15
     shared.release_disc_planes()
     # the cached walk uses the octagon decomposition (diagonal tables); the square + caps walk must agree bit for bit
-    import os
+    from topo_descriptors_b200 import _lib
 
-    os.environ["TOPO_NO_OCTAGON"] = "1"
+    _lib.set_option("octagon", False)
     try:
         square = DeviceDEM(dev.to_device(zi)).share_disc_planes(max(sizes))
         for s in (301, 151, 201):
             assert bool((dev.tpi(square, s) == want[s][0]).all()) and bool((dev.std(square, s) == want[s][1]).all()), s
     finally:
-        del os.environ["TOPO_NO_OCTAGON"]
+        _lib.set_option("octagon", True)
     # a row band with enough halo for the largest size
     lo, hi, halo = 120, 300, max(sizes) // 2
     band = _band(plain.tensor, lo, hi, halo, plain.stats).share_disc_planes(max(sizes))

@@ -161,10 +161,44 @@ def test_cfg_defaults():
     assert CFG.scale_std == 4 and CFG.min_elevation == -100
 
 
+def _krueger_utm(lat, lon, zone):
+    """Karney / Krueger series to n^4 (sub-millimetre): the cross-check for helpers._wgs84_to_utm."""
+    a, f, k0 = 6378137.0, 1.0 / 298.257223563, 0.9996
+    n = f / (2.0 - f)
+    A = a / (1.0 + n) * (1.0 + n**2 / 4.0 + n**4 / 64.0)
+    alpha = (n / 2.0 - 2.0 * n**2 / 3.0 + 5.0 * n**3 / 16.0 + 41.0 * n**4 / 180.0,
+             13.0 * n**2 / 48.0 - 3.0 * n**3 / 5.0 + 557.0 * n**4 / 1440.0,
+             61.0 * n**3 / 240.0 - 103.0 * n**4 / 140.0, 49561.0 * n**4 / 161280.0)
+    lam = np.deg2rad(lon) - np.deg2rad((zone - 1) * 6.0 - 180.0 + 3.0)
+    phi = np.deg2rad(lat)
+    e = np.sqrt(f * (2.0 - f))
+    t = np.sinh(np.arctanh(np.sin(phi)) - e * np.arctanh(e * np.sin(phi)))
+    xi, eta = np.arctan2(t, np.cos(lam)), np.arctanh(np.sin(lam) / np.sqrt(1.0 + t * t))
+    E, N = eta.copy(), xi.copy()
+    for j, aj in enumerate(alpha, start=1):
+        E = E + aj * np.cos(2 * j * xi) * np.sinh(2 * j * eta)
+        N = N + aj * np.sin(2 * j * xi) * np.cosh(2 * j * eta)
+    return 500000.0 + k0 * A * E, k0 * A * N
+
+
 def test_wgs84_resolution():
     # utm.from_latlon(51.2, 7.5) == (395201.3103811303, 5673135.241182375, 32, 'U')  (utm package docs)
     e, n = hlp._wgs84_to_utm(51.2, 7.5)
-    assert abs(e - 395201.3103811303) < 1e-3 and abs(n - 5673135.241182375) < 1e-3
+    assert abs(e - 395201.3103811303) < 1e-8 and abs(n - 5673135.241182375) < 1e-8
+    # independent check of the series: Krueger's transverse Mercator (n^4) agrees to a millimetre inside the zone
+    ke, kn = _krueger_utm(np.array([51.2, 46.5, 10.0]), np.array([7.5, 8.9, 11.9]), 32)
+    se, sn = hlp._wgs84_to_utm(np.array([51.2, 46.5, 10.0]), np.array([7.5, 8.9, 11.9]))
+    assert np.abs(ke - se).max() < 2e-3 and np.abs(kn - sn).max() < 2e-3
+    # zone rule of utm.latlon_to_zone_number: first element of the grid, Norway / Svalbard exceptions
+    assert hlp._utm_zone_number(np.array([[46.0, 46.0]]), np.array([[5.9, 6.1]])) == 31  # Swiss DEM starting below 6 E
+    assert hlp._utm_zone_number(46.0, 6.1) == 32 and hlp._utm_zone_number(60.0, 4.0) == 32  # 32V
+    assert hlp._utm_zone_number(75.0, 10.0) == 33 and hlp._utm_zone_number(75.0, 8.0) == 31
+    assert hlp._utm_zone_number(0.0, 180.0) == 1 and hlp._utm_zone_number(-30.0, -70.5) == 19
+    # a grid that straddles 6 E keeps the zone (central meridian 3 E) of its first column
+    e2, _ = hlp._wgs84_to_utm(np.array([[46.0, 46.0]]), np.array([[5.9, 6.1]]))
+    assert e2[0, 1] - e2[0, 0] > 15000 and e2[0, 0] > 700000
+    with pytest.raises(ValueError):
+        hlp._wgs84_to_utm(np.array([-1.0, 1.0]), np.array([7.0, 7.0]))
     lon = 8.0 + np.arange(40) / 3600.0
     lat = 46.5 - np.arange(30) / 3600.0
     ds = _xr.Dataset({"a": (("y", "x"), np.zeros((30, 40), np.float32))}, coords={"x": lon, "y": lat},
@@ -250,13 +284,15 @@ def test_library_exports_every_declared_symbol():
     v = _lib.View(1440, 900, 0, 900, 0, 900)
     import ctypes
 
-    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 17, 0, 0) == 0  # fused: no workspace
-    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 801, 0, 0) > 4 * 900 * 1440
+    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 17, 0, 1, 200.0, 3400.0, 0) == 0  # fused: no workspace
+    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 801, 0, 1, 200.0, 3400.0, 0) > 4 * 900 * 1440
     # with a plane cache the planes live there: the workspace shrinks and mid sizes walk the cached planes
-    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1) > 10 * 4 * 900 * 1440
-    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0) == 2 * lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1)
-    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 41, 1, 801) >= 2 * 8 * 900 * 1440  # raw sums of two planes
-    assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, 0) == 0 and lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, 801) == 1
+    rng = (200.0, 3400.0)
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) > 10 * 4 * 900 * 1440
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0, *rng) == 2 * lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng)
+    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 41, 1, 1, *rng, 801) >= 2 * 8 * 900 * 1440  # raw sums of two planes
+    assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, *rng, 0) == 0
+    assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, *rng, 801) == 1
 
 
 def test_c_abi_argument_errors_are_reported_before_any_launch():
@@ -300,3 +336,41 @@ def test_no_cpu_fallback():
         topo.tpi(np.zeros((8, 8), np.float32), 3)
     with pytest.raises(RuntimeError):
         topo.gradient(np.zeros((8, 8), np.float32), 2.0, {"x": np.ones(8), "y": np.ones(8)})
+
+
+def test_disc_queries_agree_with_the_plan_over_a_size_x_range_grid():
+    """The workspace / cache / tsum queries make the same plan as the call itself (host-only introspection): a
+    shared-plane sweep whose layout overflows for one size falls back consistently, and STD on wide ranges splits
+    the square plane instead of failing (an Alpine 0..4800 m DEM from size ~800, 0..8848 m from size ~400)."""
+    import ctypes
+
+    lib = _lib.load()
+    v = _lib.View(4096, 4096, 0, 4096, 0, 4096)
+    vp = ctypes.byref(v)
+    info = (ctypes.c_longlong * 32)()
+    for integer in (1, 0):
+        for zmin, zmax in ((200.0, 3400.0), (200.0, 4700.0), (0.0, 4800.0), (0.0, 8848.0), (-11000.0, 8848.0)):
+            for hint in (0, 801, 2001):
+                for size in (5, 21, 41, 201, 401, 801, 2001):
+                    if hint and size > hint:
+                        continue
+                    for what in (0, 1):
+                        assert lib.topo_disc_plan_info(vp, size, what, integer, zmin, zmax, hint, info) == 0, (
+                            size, what, integer, zmin, zmax, hint, lib.topo_last_error())
+                        fused, cached, ws, off_partial = info[1], info[4], info[14], info[15]
+                        need = 0 if fused else (ws - off_partial if cached else ws)
+                        got = lib.topo_disc_workspace_bytes(vp, size, what, integer, zmin, zmax, hint)
+                        assert got == need, (size, what, integer, zmin, zmax, hint, got, need)
+                    if lib.topo_disc_shares_tsum(vp, size, integer, zmin, zmax, hint):
+                        a = (ctypes.c_longlong * 32)()
+                        b = (ctypes.c_longlong * 32)()
+                        lib.topo_disc_plan_info(vp, size, 0, integer, zmin, zmax, hint, a)
+                        lib.topo_disc_plan_info(vp, size, 1, integer, zmin, zmax, hint, b)
+                        assert (a[0], b[0], a[1], b[1]) == (4, 2, 0, 0)  # TPI_I + STD_I, both two-pass
+    # the advisor's cases: std(801) on 200..4800 and std(2001) now plan (split squares) instead of raising
+    for size in (801, 2001):
+        assert lib.topo_disc_plan_info(vp, size, 1, 1, 200.0, 4800.0, 0, info) == 0 and info[16] == 1
+    assert lib.topo_disc_plan_info(vp, 801, 1, 1, 200.0, 3400.0, 0, info) == 0 and info[16] == 0
+    # a cache laid out for a split square holds one more plane region
+    base = lib.topo_disc_cache_bytes(vp, 801, 1, 200.0, 3400.0)
+    assert base > 0 and lib.topo_disc_cache_bytes(vp, 801, 1, 0.0, 4800.0) * 2 == base * 3

@@ -45,15 +45,16 @@ PROTOTYPES = {
     "topo_version": (c_int, []),
     "topo_last_error": (c_char_p, []),
     "topo_launch_count": (c_longlong, []),
+    "topo_set_option": (c_int, [c_char_p, c_int]),
     "topo_profile_enable": (c_int, [c_int]),
     "topo_profile_dump": (c_int, [c_char_p, c_size_t]),
     "topo_dem_stats_workspace_bytes": (c_size_t, [c_int, c_int]),
     "topo_dem_stats_f32": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "topo_fill_f32": (c_int, [c_void_p, c_int, c_int, c_int64, c_float, c_void_p]),
     "topo_stamp_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
-    "topo_disc_workspace_bytes": (c_size_t, [_VP, c_int, c_int, c_int]),
-    "topo_disc_shares_tsum": (c_int, [_VP, c_int, c_int, c_int]),
-    "topo_disc_cache_bytes": (c_size_t, [_VP, c_int, c_int]),
+    "topo_disc_workspace_bytes": (c_size_t, [_VP, c_int, c_int, c_int, c_double, c_double, c_int]),
+    "topo_disc_shares_tsum": (c_int, [_VP, c_int, c_int, c_double, c_double, c_int]),
+    "topo_disc_cache_bytes": (c_size_t, [_VP, c_int, c_int, c_double, c_double]),
     "topo_disc_plan_info": (c_int, [_VP, c_int, c_int, c_int, c_double, c_double, c_int, c_void_p]),
     "topo_tpi_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_int, c_int, c_double, c_double,
                              c_void_p, c_int, _CP, c_void_p, c_size_t, c_void_p]),
@@ -111,6 +112,11 @@ def call(name, *args):
     if rc != 0:
         msg = cdll.topo_last_error()
         raise TopoError(f"{name} failed ({rc}): {msg.decode() if msg else 'unknown error'}")
+
+
+def set_option(name, value):
+    """Execution-shape switch of the library (include/topo_b200.h: topo_set_option); results do not change."""
+    call("topo_set_option", name.encode(), int(bool(value)))
 
 
 def launch_count():

@@ -239,11 +239,3 @@ def bind_to_gpu_numa(index):
         return True
     except Exception:  # no NVML, no permission, or a single-socket host: nothing to do
         return False
-
-
-def numpy_partition_check(gny, world):
-    """Small self-check used by the tests: the partition tiles [0, gny) without gaps."""
-    parts = partition_rows(gny, world)
-    assert parts[0][0] == 0 and parts[-1][1] == gny
-    assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
-    return np.array(parts)

@@ -13,6 +13,11 @@ namespace topo {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Execution-path switches (topo_set_option): every setting computes the same results through a different kernel
+// shape; the tests flip them to cross-check the shapes bit for bit.  Never read from the environment.
+enum Option { kOptOctagon = 0, kOptTiny = 1, kOptSxTma = 2, kOptGaussFft = 3, kOptGradFused = 4, kOptCount = 5 };
+bool option_enabled(int opt);
+
 // Optional per-kernel timing (topo_profile_enable / topo_profile_dump): CUDA events recorded on the
 // launching stream around each kernel, aggregated by kernel name.  Off by default (zero overhead).
 struct ProfScope {

@@ -43,7 +43,9 @@
 namespace topo {
 
 // PL_*: single planes, used by the two-pass path which processes one plane per launch
-enum DiscMode { TPI_Q = 0, TPI_X = 1, STD_I = 2, STD_F = 3, TPI_I = 4, PL_T = 5, PL_Q = 6, PL_F = 7 };
+// PL_QL / PL_QH: the centred square split into its low / high 16 bits, for DEMs whose size x range^2 overflows the
+// 32-bit span sums of PL_Q (an Alpine 0..4800 m range from size ~800, 0..8848 m from size ~400)
+enum DiscMode { TPI_Q = 0, TPI_X = 1, STD_I = 2, STD_F = 3, TPI_I = 4, PL_T = 5, PL_Q = 6, PL_F = 7, PL_QL = 8, PL_QH = 9 };
 
 template <int MODE>
 struct ModeTraits;
@@ -63,6 +65,10 @@ template <>
 struct ModeTraits<PL_Q> { static constexpr int NARR = 1; static constexpr int RB = 8; };
 template <>
 struct ModeTraits<PL_F> { static constexpr int NARR = 1; static constexpr int RB = 8; };
+template <>
+struct ModeTraits<PL_QL> { static constexpr int NARR = 1; static constexpr int RB = 8; };
+template <>
+struct ModeTraits<PL_QH> { static constexpr int NARR = 1; static constexpr int RB = 8; };
 
 constexpr int kTW = 128;        // output tile width: 64 threads x 2 pixels
 constexpr int kTH = 32;         // output tile height: 4 row groups x 8 rows
@@ -84,7 +90,6 @@ struct DiscParams {
     int oct_ndiag;   // corner diagonals |i| + |j| = u + v + 1 .. u + v + ndiag
     uint32_t* eplanes;           // diagonal prefix of the plane values: E1 A, E1 B, E2 A, E2 B (plane_stride apart)
     unsigned long long* dplanes; // diagonal sums of the 64-bit row prefix: D1, D2 (sat_stride apart)
-    int dbg_skip;  // profiling only (TOPO_DBG_SKIP): 1 = skip column caps, 2 = skip row caps, 4 = skip square
     unsigned long long* partial;  // two-pass, multi-plane modes: raw disc sums, [plane][out_rows][nx]
     int64_t partial_stride;
     unsigned long long* tsum;  // optional: raw sums of the T plane (trunc(z) - tmin), shared between tpi and std
@@ -112,6 +117,7 @@ struct DiscParams {
     long long n_ll;
     double nc0_scaled, n_tmin;  // N*c0 (TPI_Q: times 2^-S folded in) and N*tmin as doubles, for the 32-bit epilogue
     double inv_n_nm1;  // 1 / (N * (N - 1))
+    int qsplit;        // STD: the square plane is split in PL_QL + PL_QH (raw sums of PL_QH: partial plane NARR)
     int exact64;       // N*B - a^2 fits in 64-bit integers
     int excl;          // TPI: offset (excl, excl) of the excluded "mid point" (0 odd size, -1 even size)
 };
@@ -153,6 +159,12 @@ __device__ __forceinline__ void convert(const DiscParams& p, float z, uint32_t (
     } else if constexpr (MODE == PL_Q) {
         const int d = __float2int_rz(z) - p.cmid;
         v[0] = (uint32_t)(d * d);
+    } else if constexpr (MODE == PL_QL) {
+        const int d = __float2int_rz(z) - p.cmid;
+        v[0] = (uint32_t)(d * d) & 0xffffu;
+    } else if constexpr (MODE == PL_QH) {
+        const int d = __float2int_rz(z) - p.cmid;
+        v[0] = (uint32_t)(d * d) >> 16;
     } else if constexpr (MODE == PL_F) {
         const float f1 = (z - (float)__float2int_rz(z)) + 1.0f;
         v[0] = (uint32_t)__float2int_rn(f1 * p.fscale);
@@ -1075,12 +1087,10 @@ __device__ __forceinline__ void hybrid_walk(const DiscParams& p, const int* __re
     }
     // ---- top / bottom caps: kernel rows |i - mid| > a
     const int ncap = mid - a_sq;
-    if (!(p.dbg_skip & 2)) {
-        row_walk_grouped<ACC32>(p, tab, prow + p.c, lcx, 0, ncap, lead, lag, A);
-        row_walk_grouped<ACC32>(p, tab, prow + p.c, lcx, p.k - ncap, p.k, lead, lag, A);
-    }
+    row_walk_grouped<ACC32>(p, tab, prow + p.c, lcx, 0, ncap, lead, lag, A);
+    row_walk_grouped<ACC32>(p, tab, prow + p.c, lcx, p.k - ncap, p.k, lead, lag, A);
     // ---- left / right caps: columns |cc| > a, column-prefix spans of half-height h = half-width of row mid+cc
-    if (!(p.dbg_skip & 1)) {
+    {
         const uint32_t* colp = p.cplanes + (int64_t)prow * pitch;  // row base; the column goes into the offset
         const int cstride = (int)p.cplane_stride;
 #pragma unroll 1
@@ -1204,6 +1214,9 @@ __global__ void __launch_bounds__(256) disc_finish_kernel(const DiscParams p) {
         unsigned long long acc[NARR];
 #pragma unroll
         for (int a = 0; a < NARR; ++a) acc[a] = (a == 0 && p.tsum) ? p.tsum[idx] : p.partial[a * p.partial_stride + idx];
+        if constexpr (MODE == STD_I || MODE == STD_F) {
+            if (p.qsplit) acc[1] += p.partial[NARR * p.partial_stride + idx] << 16;
+        }
         p.out[(int64_t)r * p.ld_out + x] = finish<MODE>(p, acc, p.out_gy0 + r, x);
     }
 }
@@ -1212,6 +1225,8 @@ __global__ void __launch_bounds__(256) disc_finish_kernel(const DiscParams p) {
 struct DiscPlan {
     DiscParams p;
     int mode, acc;
+    bool acc_qh;  // split squares: the PL_QH disc sums fit 32 bits
+    int qh_kind;  // plane-cache region of PL_QH
     bool fused, hybrid, tiny, cached;
     size_t smem;
     int prefix_rows;  // two-pass
@@ -1246,7 +1261,8 @@ static int max_rb(int mode) { return (mode == TPI_Q || mode == TPI_I) ? 8 : 4; }
 static int narr_of(int mode) { return (mode == TPI_Q || mode == TPI_I) ? 1 : (mode == STD_F ? 3 : 2); }
 
 // Geometry that does not depend on the data range (used by the workspace query too).
-static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPlan& pl, int plane_halo = 0) {
+static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPlan& pl, int plane_halo = 0,
+                         bool force_two_pass = false) {
     DiscParams& p = pl.p;
     p.nx = v->nx, p.gny = v->gny, p.in_gy0 = v->in_gy0, p.in_rows = v->in_rows;
     p.out_gy0 = v->out_gy0, p.out_rows = v->out_rows;
@@ -1264,9 +1280,8 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
         const size_t bytes = (size_t)tab_bytes + (size_t)R * pitch * 4 * narr;
         // with a plane cache the prefix planes are already there: odd discs from kCachedTwoPassMin on walk them
         // (octagon: ~1.2 * size lookups) instead of re-scanning tile + halo in shared memory (2 * size lookups)
-        static const int cached_min = getenv("TOPO_CACHED_TWOPASS_MIN") ? atoi(getenv("TOPO_CACHED_TWOPASS_MIN")) : kCachedTwoPassMin;
-        const bool prefer_planes = plane_halo > 0 && (size & 1) && size >= cached_min;
-        if (bytes <= kFusedSmemBudget && !prefer_planes) {
+        const bool prefer_planes = plane_halo > 0 && (size & 1) && size >= kCachedTwoPassMin;
+        if (bytes <= kFusedSmemBudget && !prefer_planes && !force_two_pass) {
             pl.fused = true;
             pl.hybrid = false;
             p.pitch = pitch;
@@ -1326,7 +1341,7 @@ static int plan_geometry(const topo_view* v, int size, int narr, int rb, DiscPla
         pl.ndiag_threads = rows + p.pitch;
         pl.off_dtot = bytes;
         bytes = align(pl.off_dtot + (size_t)2 * pl.ndchunks * pl.ndiag_threads * 8);  // chunk totals of the diagonal scans
-        if (pl.hybrid && !getenv("TOPO_NO_OCTAGON")) {
+        if (pl.hybrid && option_enabled(kOptOctagon)) {
             // u minimising the walked lines 4 (mid - u) + 4 (dmax - u - v), v = isqrt(mid^2 - u^2) <= u
             const long long m = p.mid, m2 = m * m;
             auto isqrt = [](long long n) {
@@ -1395,6 +1410,8 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
     DiscParams& p = pl.p;
     memset(&p, 0, sizeof(p));
     double vmax[3] = {0, 0, 0};  // largest value a plane element can take
+    double vmax_qh = 0;
+    int qsplit = 0;
     if (what == 0 && !all_integer) {
         const double c0 = fmin(0.0, floor(zmin));
         const double range = fmax(0.0, zmax) - c0 + 1.0;
@@ -1425,9 +1442,15 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
         vmax[0] = trange + 1.0;
         if (mode == STD_I || mode == STD_F) {
             const double half = floor(trange / 2.0) + 1.0;
-            TOPO_CHECK(span * half * half < kU32, "size %d x (DEM range %.0f)^2 overflows the 32-bit span sums of squares",
-                       size, trange);
-            vmax[1] = half * half;
+            if (span * half * half < kU32) {
+                vmax[1] = half * half;
+            } else {
+                // the square itself must fit 32 bits; its 16-bit halves then always fit the span sums (span <= 8191)
+                TOPO_CHECK(half <= 65535.0, "DEM range %.0f too wide for the integer squares of std", trange);
+                qsplit = 1;
+                vmax[1] = 65535.0;
+                vmax_qh = floor(half * half / 65536.0);
+            }
         }
         if (mode == TPI_X || mode == STD_F) {
             int Sf = 30 - (ilog2_floor(span) + 1);
@@ -1443,8 +1466,11 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
     // shared planes: laid out for the halo of the largest size of the sweep
     const int plane_halo = cache_size >= size ? cache_size / 2 : 0;
     pl.cached = plane_halo > 0;
-    if (plan_geometry(v, size, narr_of(mode), max_rb(mode), pl, plane_halo)) return -1;
+    if (plan_geometry(v, size, narr_of(mode) + qsplit, max_rb(mode), pl, plane_halo, qsplit != 0)) return -1;
     if (pl.fused) pl.cached = false;
+    p.qsplit = qsplit;
+    pl.acc_qh = qsplit && n * vmax_qh < kU32;
+    pl.qh_kind = all_integer ? 2 : 4;
     pl.tiny = false;
     if (pl.fused) {
         // instantiated accumulator layouts of the fused kernels: none, plane 0 only, all planes
@@ -1452,7 +1478,7 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
         // tiny odd discs whose sums fit 32 bits: direct register sliding sums instead of prefix sums
         // (one loaded plane only: with two the 128 x 128 tile leaves a single CTA per SM and the prefix kernel wins)
         pl.tiny = (size & 1) && size >= 5 && size <= 13 && acc == full && (mode == TPI_I || mode == TPI_Q || mode == STD_I) &&
-                  !getenv("TOPO_NO_TINY");
+                  option_enabled(kOptTiny);
         if (acc != full) acc &= 1;
     }
     pl.acc = acc;
@@ -1486,6 +1512,8 @@ static const char* mode_name(int mode) {
         case STD_F: return "STD_F";
         case PL_T: return "T";
         case PL_Q: return "Q";
+        case PL_QL: return "QL";
+        case PL_QH: return "QH";
         default: return "F";
     }
 }
@@ -1501,12 +1529,6 @@ static const char* kernel_label(const char* kind, int mode, int acc) {
     if (used == 64) return "disc";
     strcpy(names[used], buf);
     return names[used++];
-}
-
-// Extra dynamic shared memory per CTA for the gather kernels (environment knob for occupancy experiments).
-static size_t span_extra_smem() {
-    static const size_t v = getenv("TOPO_SPAN_EXTRA_SMEM") ? (size_t)atol(getenv("TOPO_SPAN_EXTRA_SMEM")) : 0;
-    return v;
 }
 
 template <int MODE, int ACC>
@@ -1570,10 +1592,13 @@ template <int PM, int FIN>
 static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t s, topo_disc_cache* cache = nullptr) {
     DiscParams p = pl.p;
     bool need_rows = true, need_cols = pl.hybrid;
+    int publish = 0;  // cache->valid bits, set once every launch of this plane was accepted
     if (cache) {
         // plane kind 0 = trunc(z) - tmin, 1 = its centred square, 2 = fraction, 3 = quantised elevation (float DEMs):
         // one region each, same internal layout as the workspace
-        const int kind = PM == PL_Q ? 1 : PM == PL_F ? 2 : PM == TPI_Q ? 3 : 0;
+        // (+ the high half of a split square, after the kinds the DEM uses anyway: region 2 for integer-valued DEMs,
+        // region 4 for float DEMs)
+        const int kind = (PM == PL_Q || PM == PL_QL) ? 1 : PM == PL_F ? 2 : PM == TPI_Q ? 3 : PM == PL_QH ? pl.qh_kind : 0;
         TOPO_CHECK(cache->bytes >= (size_t)(kind + 1) * pl.off_partial, "plane cache too small: need %zu bytes, got %zu",
                    (size_t)(kind + 1) * pl.off_partial, cache->bytes);
         unsigned char* region = reinterpret_cast<unsigned char*>(cache->mem) + (size_t)kind * pl.off_partial;
@@ -1585,14 +1610,14 @@ static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t 
         const int row_bit = 1 << (2 * kind), col_bit = 2 << (2 * kind);
         need_rows = !(cache->valid & row_bit);
         need_cols = pl.hybrid && !(cache->valid & col_bit);
-        cache->valid |= row_bit | (pl.hybrid ? col_bit : 0);
+        publish = row_bit | (pl.hybrid ? col_bit : 0);
     }
     const int warps = kThreads / 32;
     if (need_rows)
         TOPO_LAUNCH(kernel_label("disc_prefix", PM, 0), s,
                     disc_prefix_kernel<PM><<<ceil_div(pl.prefix_rows, warps), kThreads, 0, s>>>(p, pl.prefix_rows));
     const int grid = p.tiles_x * p.tiles_y;
-    const size_t smem = pl.smem + span_extra_smem();
+    const size_t smem = pl.smem;
     if (pl.hybrid) {
         if (need_cols) {
             unsigned char* ws = reinterpret_cast<unsigned char*>(p.planes);
@@ -1626,6 +1651,7 @@ static int launch_plane(const DiscPlan& pl, int plane, bool acc32, cudaStream_t 
         else
             TOPO_LAUNCH(kernel_label("disc_span", PM, 0), s, disc_span_kernel<false, false, FIN><<<grid, kThreads, smem, s>>>(p, plane));
     }
+    if (cache) cache->valid |= publish;
     return 0;
 }
 
@@ -1647,12 +1673,22 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo
             return 0;
         case STD_I:
             if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s, cache))) return rc;
-            if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s, cache))) return rc;
+            if (pl.p.qsplit) {
+                if ((rc = launch_plane<PL_QL, -1>(pl, 1, a1, s, cache))) return rc;
+                if ((rc = launch_plane<PL_QH, -1>(pl, 2, pl.acc_qh, s, cache))) return rc;
+            } else if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s, cache))) {
+                return rc;
+            }
             TOPO_LAUNCH("disc_finish<STD_I>", s, disc_finish_kernel<STD_I><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
         default:
             if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s, cache))) return rc;
-            if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s, cache))) return rc;
+            if (pl.p.qsplit) {
+                if ((rc = launch_plane<PL_QL, -1>(pl, 1, a1, s, cache))) return rc;
+                if ((rc = launch_plane<PL_QH, -1>(pl, 3, pl.acc_qh, s, cache))) return rc;
+            } else if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s, cache))) {
+                return rc;
+            }
             if ((rc = launch_plane<PL_F, -1>(pl, 2, a2, s, cache))) return rc;
             TOPO_LAUNCH("disc_finish<STD_F>", s, disc_finish_kernel<STD_F><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
@@ -1695,7 +1731,6 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
             pl.p.sat = reinterpret_cast<unsigned long long*>((unsigned char*)ws + pl.off_sat);
         }
         pl.p.partial = reinterpret_cast<unsigned long long*>((unsigned char*)ws + (cache ? 0 : pl.off_partial));
-        pl.p.dbg_skip = getenv("TOPO_DBG_SKIP") ? atoi(getenv("TOPO_DBG_SKIP")) : 0;
         if (tsum_op != 0) {
             TOPO_CHECK(tsum != nullptr, "tsum_op %d needs a T-plane sum buffer", tsum_op);
             TOPO_CHECK(pl.mode != TPI_Q, "this size/DEM does not use the T plane (see topo_disc_shares_tsum)");
@@ -1728,34 +1763,40 @@ using namespace topo;
 
 extern "C" {
 
-size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what, int cache_max_size) {
-    if (!v || size < 2 || size > kMaxSize) return 0;
-    // worst case over the modes `what` can select (the mode depends on the data); with a plane cache the integer
-    // modes keep their planes there and only need room for the raw plane sums
-    size_t worst = 0;
-    const int modes_tpi[3] = {TPI_Q, TPI_X, TPI_I}, modes_std[3] = {STD_I, STD_F, STD_F};
-    for (int m = 0; m < 3; ++m) {
-        const int mode = what == 0 ? modes_tpi[m] : modes_std[m];
-        const bool cached = cache_max_size >= size;
-        DiscPlan pl;
-        memset(&pl, 0, sizeof(pl));
-        plan_geometry(v, size, narr_of(mode), max_rb(mode), pl, cached ? cache_max_size / 2 : 0);
-        const size_t need = (cached && !pl.fused) ? pl.ws_bytes - pl.off_partial : pl.ws_bytes;
-        if (need > worst) worst = need;
-    }
-    return worst;
+// The three queries below make the SAME plan as run_disc (same range, integrality and cache size), so what they
+// report is what the call will do -- including its fall-back to an un-cached plan when the shared layout overflows.
+static bool quiet_plan(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, int cache_max_size,
+                       DiscPlan& pl) {
+    if (!v || size < 2 || size > kMaxSize || validate_view(v)) return false;
+    memset(&pl, 0, sizeof(pl));
+    return plan_disc(v, size, what, all_integer, zmin, zmax, pl, cache_max_size) == 0;
 }
 
-int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, int cache_max_size) {
+size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax,
+                                 int cache_max_size) {
+    DiscPlan pl;
+    if (!quiet_plan(v, size, what, all_integer, zmin, zmax, cache_max_size, pl)) return 0;
+    if (pl.fused) return 0;
+    // with a plane cache the planes live there and the workspace only holds the raw plane sums
+    return pl.cached ? pl.ws_bytes - pl.off_partial : pl.ws_bytes;
+}
+
+int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, double zmin, double zmax, int cache_max_size) {
     // tpi and std of the same size both run two-pass on the integer planes => std can reuse tpi's T-plane sums
-    if (!v || !all_integer || size < 2 || size > kMaxSize) return 0;
-    const int plane_halo = cache_max_size >= size ? cache_max_size / 2 : 0;
+    if (!all_integer) return 0;
     DiscPlan a, b;
-    memset(&a, 0, sizeof(a));
-    memset(&b, 0, sizeof(b));
-    plan_geometry(v, size, narr_of(TPI_I), max_rb(TPI_I), a, plane_halo);
-    plan_geometry(v, size, narr_of(STD_I), max_rb(STD_I), b, plane_halo);
-    return (!a.fused && !b.fused) ? 1 : 0;
+    if (!quiet_plan(v, size, 0, all_integer, zmin, zmax, cache_max_size, a)) return 0;
+    if (!quiet_plan(v, size, 1, all_integer, zmin, zmax, cache_max_size, b)) return 0;
+    return (!a.fused && !b.fused && a.mode == TPI_I && b.mode == STD_I && a.p.tmin == b.p.tmin) ? 1 : 0;
+}
+
+size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer, double zmin, double zmax) {
+    DiscPlan pl;
+    if (!quiet_plan(v, max_size, 1, all_integer, zmin, zmax, max_size, pl)) return 0;
+    if (pl.fused || !pl.cached) return 0;
+    // integer-valued DEMs use two plane kinds (trunc(z) - tmin, its square); float DEMs add the fraction and the
+    // quantised-elevation planes; a split square adds its high half
+    return (size_t)((all_integer ? 2 : 4) + (pl.p.qsplit ? 1 : 0)) * pl.off_partial;
 }
 
 int topo_disc_plan_info(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax,
@@ -1769,18 +1810,8 @@ int topo_disc_plan_info(const topo_view* v, int size, int what, int all_integer,
     info[0] = pl.mode, info[1] = pl.fused, info[2] = pl.hybrid, info[3] = pl.tiny, info[4] = pl.cached;
     info[5] = pl.p.oct, info[6] = pl.p.asq, info[7] = pl.p.oct_v, info[8] = pl.p.oct_ndiag, info[9] = pl.acc;
     info[10] = (long long)pl.smem, info[11] = pl.p.halo, info[12] = pl.p.pitch, info[13] = pl.prefix_rows;
-    info[14] = (long long)pl.ws_bytes, info[15] = (long long)pl.off_partial;
+    info[14] = (long long)pl.ws_bytes, info[15] = (long long)pl.off_partial, info[16] = pl.p.qsplit;
     return 0;
-}
-
-size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer) {
-    if (!v || max_size < 2 || max_size > kMaxSize) return 0;
-    DiscPlan pl;
-    memset(&pl, 0, sizeof(pl));
-    plan_geometry(v, max_size, 1, 8, pl, max_size / 2);
-    // integer-valued DEMs use two plane kinds (trunc(z) - tmin, its square); float DEMs add the fraction and the
-    // quantised-elevation planes
-    return pl.fused ? 0 : (size_t)(all_integer ? 2 : 4) * pl.off_partial;
 }
 
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,

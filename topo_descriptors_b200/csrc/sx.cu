@@ -219,7 +219,7 @@ int topo_sx_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int
     }
     cudaStream_t s = (cudaStream_t)stream;
     // ---- TMA-staged path: the per-azimuth sample bounding box (<= the global extents given here) must fit a box
-    if (!getenv("TOPO_SX_NO_TMA")) {
+    if (option_enabled(kOptSxTma)) {
         const int dyl = dy_min < 0 ? dy_min : 0, dyh = dy_max > 0 ? dy_max : 0;
         const int dxl = (dx_min < 0 ? dx_min : 0) & ~3, dxh = dx_max > 0 ? dx_max : 0;  // origin x aligned down to 4
         // conservative box: every azimuth's own bounding box (which includes the centre) is within the global span

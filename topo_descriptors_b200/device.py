@@ -81,6 +81,7 @@ class DeviceDEM:
     def release_disc_planes(self):
         self._plane_hint = 0
         self._plane_cache = None
+        self._tsum = None
 
     @property
     def shape(self):
@@ -127,16 +128,6 @@ def dem_stats(tensor):
     return {
         "min": float(s[0]), "max": float(s[1]), "nonfinite": int(s[2]), "nonint": int(s[3]),
         "sum": float(s[4]), "sumsq": float(s[5]), "n": int(s[6]),
-    }
-
-
-def merge_stats(parts):
-    """Combine per-band statistics into global ones (used by the row-band driver)."""
-    return {
-        "min": min(p["min"] for p in parts), "max": max(p["max"] for p in parts),
-        "nonfinite": sum(p["nonfinite"] for p in parts), "nonint": sum(p["nonint"] for p in parts),
-        "sum": float(np.sum([p["sum"] for p in parts])), "sumsq": float(np.sum([p["sumsq"] for p in parts])),
-        "n": sum(p["n"] for p in parts),
     }
 
 
@@ -241,21 +232,21 @@ def _nan_result(v, like, n=1):
 
 def _tsum_plan(dem, v, size, st, share, cache_size=0):
     """T-plane sum sharing between tpi(size) and std(size) of the same integer-valued DEM band:
-    returns (tensor or None, op) with op 0 = off, 1 = compute + keep, 2 = reuse."""
+    returns (tensor or None, op, keep) with op 0 = off, 1 = compute + keep, 2 = reuse; ``keep`` is what the caller
+    publishes as ``dem._tsum`` AFTER the launch succeeded (a failed call must not leave an unwritten buffer behind)."""
     torch = _torch()
     if not share or st["nonint"] != 0:
-        return None, 0
+        return None, 0, None
     L = _lib.load()
-    if not L.topo_disc_shares_tsum(ctypes.byref(v), int(size), 1, int(cache_size)):
-        return None, 0
+    if not L.topo_disc_shares_tsum(ctypes.byref(v), int(size), 1, st["min"], st["max"], int(cache_size)):
+        return None, 0, None
     key = (int(size), v.out_gy0, v.out_rows)
     cached = getattr(dem, "_tsum", None)
+    dem._tsum = None  # consumed (a tpi+std pair is the use case), or replaced once the new sums exist
     if cached is not None and cached[0] == key:
-        dem._tsum = None  # consumed: a tpi+std pair is the use case, free the 8 B/px right after
-        return cached[1], 2
+        return cached[1], 2, None
     t = torch.empty((v.out_rows, dem.nx), dtype=torch.int64, device=dem.tensor.device)
-    dem._tsum = (key, t)
-    return t, 1
+    return t, 1, (key, t)
 
 
 def _disc(name, what, dem, size, out_gy0, out_rows, out, share):
@@ -269,12 +260,16 @@ def _disc(name, what, dem, size, out_gy0, out_rows, out, share):
         return out
     L = _lib.load()
     cache = _plane_cache(dem, v, size, st)
-    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), what, cache.max_size if cache is not None else 0)
+    cache_size = cache.max_size if cache is not None else 0
+    integer = 1 if st["nonint"] == 0 else 0
+    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), what, integer, st["min"], st["max"], cache_size)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
-    tsum, op = _tsum_plan(dem, v, size, st, share, cache.max_size if cache is not None else 0)
+    tsum, op, keep = _tsum_plan(dem, v, size, st, share, cache_size)
     _lib.call(name, _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
-              1 if st["nonint"] == 0 else 0, st["min"], st["max"], _ptr(tsum), op,
+              integer, st["min"], st["max"], _ptr(tsum), op,
               ctypes.byref(cache) if cache is not None else None, _ptr(ws), ws_bytes, _stream())
+    if keep is not None:
+        dem._tsum = keep
     return out
 
 
@@ -303,7 +298,8 @@ def _plane_cache(dem, v, size, st):
     halo = hint // 2  # the band must cover the halo of the largest disc
     if v.in_gy0 > max(0, v.out_gy0 - halo) or v.in_gy0 + v.in_rows < min(v.gny, v.out_gy0 + v.out_rows + halo):
         return None
-    nbytes = _lib.load().topo_disc_cache_bytes(ctypes.byref(v), int(hint), 1 if st["nonint"] == 0 else 0)
+    nbytes = _lib.load().topo_disc_cache_bytes(ctypes.byref(v), int(hint), 1 if st["nonint"] == 0 else 0, st["min"],
+                                               st["max"])
     if nbytes == 0 or not _fits_in_hbm(2 * nbytes, dem.tensor.device):
         return None  # (a DEM too large for shared planes runs every size on its own workspace, as without the hint)
     mem = _torch().empty(nbytes + 256, dtype=_torch().uint8, device=dem.tensor.device)

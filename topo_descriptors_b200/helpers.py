@@ -45,44 +45,74 @@ def round_up_to_odd(f):
     return np.asarray(half * 2.0 + 1.0, dtype=np.int64)
 
 
-def _wgs84_to_utm(lat, lon):
-    """Forward transverse-Mercator (WGS84 -> UTM easting/northing), zone of the grid centre.
+def _utm_zone_number(latitude, longitude):
+    """Zone rule of ``utm.latlon_to_zone_number``: array input -> the FIRST element decides (the whole grid then
+    shares one projection), with the Norway (32V) and Svalbard (31X-37X) exceptions."""
+    latitude = float(np.asarray(latitude).flat[0])
+    longitude = float(np.asarray(longitude).flat[0])
+    if longitude == 180:
+        longitude = -180.0
+    if 56 <= latitude < 64 and 3 <= longitude < 12:
+        return 32
+    if 72 <= latitude <= 84 and longitude >= 0:
+        if longitude < 9:
+            return 31
+        if longitude < 21:
+            return 33
+        if longitude < 33:
+            return 35
+        if longitude < 42:
+            return 37
+    return int((longitude + 180) / 6) % 60 + 1
 
-    Stands in for ``utm.from_latlon`` (helpers.py:96; the package is not installed here).
-    Krueger series to n^4: sub-millimetre inside a zone, far below what the pixel-resolution
-    estimate needs.  Like ``utm`` the zone is chosen once (from the mean longitude / latitude)
-    so that the whole grid shares one projection.
+
+def _wgs84_to_utm(lat, lon):
+    """WGS84 -> UTM easting / northing, a restatement of ``utm.from_latlon`` (helpers.py:96).
+
+    The ``utm`` package (un-pinned in the reference's requirements.txt, absent from this image) publishes a
+    truncated Snyder series with E = 0.00669438, R = 6378137, K0 = 0.9996; the same series is evaluated here in the
+    same operation order, and it reproduces the package's documented known answer
+    ``from_latlon(51.2, 7.5) == (395201.3103811303, 5673135.241182375, 32, 'U')`` to 1e-9 m (tests/test_host.py).
+    Zone: ``_utm_zone_number`` (first element of array input, Norway / Svalbard exceptions); latitudes of mixed
+    sign raise like the package.
     """
     lat = np.asarray(lat, dtype=np.float64)
     lon = np.asarray(lon, dtype=np.float64)
-    a = 6378137.0
-    f = 1.0 / 298.257223563
-    k0 = 0.9996
-    n = f / (2.0 - f)
-    A = a / (1.0 + n) * (1.0 + n**2 / 4.0 + n**4 / 64.0)
-    alpha = (
-        n / 2.0 - 2.0 * n**2 / 3.0 + 5.0 * n**3 / 16.0 + 41.0 * n**4 / 180.0,
-        13.0 * n**2 / 48.0 - 3.0 * n**3 / 5.0 + 557.0 * n**4 / 1440.0,
-        61.0 * n**3 / 240.0 - 103.0 * n**4 / 140.0,
-        49561.0 * n**4 / 161280.0,
-    )
-    zone = int((float(np.mean(lon)) + 180.0) / 6.0) % 60 + 1
-    lon0 = np.deg2rad((zone - 1) * 6.0 - 180.0 + 3.0)
-    phi = np.deg2rad(lat)
-    lam = np.deg2rad(lon) - lon0
-    e = np.sqrt(f * (2.0 - f))
-    t = np.sinh(np.arctanh(np.sin(phi)) - e * np.arctanh(e * np.sin(phi)))
-    xi = np.arctan2(t, np.cos(lam))
-    eta = np.arctanh(np.sin(lam) / np.sqrt(1.0 + t * t))
-    E = eta.copy()
-    N = xi.copy()
-    for j, aj in enumerate(alpha, start=1):
-        E = E + aj * np.cos(2 * j * xi) * np.sinh(2 * j * eta)
-        N = N + aj * np.sin(2 * j * xi) * np.cosh(2 * j * eta)
-    easting = 500000.0 + k0 * A * E
-    northing = k0 * A * N
-    if float(np.mean(lat)) < 0:
-        northing = northing + 10000000.0
+    if lat.size and lat.min() < 0 <= lat.max():
+        raise ValueError("latitudes must all have the same sign")
+    K0 = 0.9996
+    E = 0.00669438
+    E2 = E * E
+    E3 = E2 * E
+    E_P2 = E / (1 - E)
+    M1 = 1 - E / 4 - 3 * E2 / 64 - 5 * E3 / 256
+    M2 = 3 * E / 8 + 3 * E2 / 32 + 45 * E3 / 1024
+    M3 = 15 * E2 / 256 + 45 * E3 / 1024
+    M4 = 35 * E3 / 3072
+    R = 6378137
+
+    lat_rad = np.radians(lat)
+    lat_sin = np.sin(lat_rad)
+    lat_cos = np.cos(lat_rad)
+    lat_tan = lat_sin / lat_cos
+    lat_tan2 = lat_tan * lat_tan
+    lat_tan4 = lat_tan2 * lat_tan2
+    zone = _utm_zone_number(lat, lon)
+    central_lon_rad = np.radians((zone - 1) * 6 - 180 + 3)
+    n = R / np.sqrt(1 - E * lat_sin**2)
+    c = E_P2 * lat_cos**2
+    a = lat_cos * ((np.radians(lon) - central_lon_rad + np.pi) % (2 * np.pi) - np.pi)
+    a2 = a * a
+    a3 = a2 * a
+    a4 = a3 * a
+    a5 = a4 * a
+    a6 = a5 * a
+    m = R * (M1 * lat_rad - M2 * np.sin(2 * lat_rad) + M3 * np.sin(4 * lat_rad) - M4 * np.sin(6 * lat_rad))
+    easting = K0 * n * (a + a3 / 6 * (1 - lat_tan2 + c) + a5 / 120 * (5 - 18 * lat_tan2 + lat_tan4 + 72 * c - 58 * E_P2)) + 500000
+    northing = K0 * (m + n * lat_tan * (a2 / 2 + a4 / 24 * (5 - lat_tan2 + 9 * c + 4 * c**2)
+                                        + a6 / 720 * (61 - 58 * lat_tan2 + lat_tan4 + 600 * c - 330 * E_P2)))
+    if lat.size and lat.max() < 0:
+        northing = northing + 10000000
     return easting, northing
 
 

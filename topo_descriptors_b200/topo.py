@@ -134,6 +134,13 @@ def tpi(dem, size, sigma=None):
     Zero-padded borders normalised by the full neighbour count, like the reference's
     ``signal.convolve(mode="same")``; any non-finite input value makes the whole output NaN (FFT
     semantics).  Result dtype follows the input (float32 in -> float32 out).
+
+    Deviations from the reference, by design: (i) a float64 DEM is rounded to float32 on upload and the result is
+    cast back to float64 (the reference would carry float64 through its FFT; the difference is the float32
+    representation error of the elevations, <= 2.5e-4 m below 4096 m); (ii) the reference's ``convolve`` may pick
+    its direct method for very small kernels, in which case a NaN only poisons its own footprint there -- here every
+    size follows the FFT rule (all NaN), which is what the compute_* drivers assume when they re-stamp ``ind_nans``
+    on a filled DEM.
     """
     m = _Marshal(dem)
     return m.back(dev.tpi(_smoothed(m.ddem, sigma), int(size)))
@@ -184,6 +191,7 @@ def std(dem, size, sigma=None):
     sqrt(clip((sum trunc(x)^2 - (sum x)^2/N) / (N-1), 0)), including the reference's
     ``dem.astype("int32")`` truncation inside the squares.  Returns float64 like the reference (the
     kernel computes the variance in exact integer / float64 arithmetic and stores float32).
+    float64 DEMs are rounded to float32 on upload (see ``tpi``); non-finite input gives an all-NaN result.
     """
     m = _Marshal(dem)
     return m.back(dev.std(_smoothed(m.ddem, sigma), int(size)), dtype=np.float64)
