@@ -74,6 +74,10 @@ int topo_profile_dump(char* buf, size_t cap);
  * through another kernel shape (the tests flip them to compare shapes bit for bit); nothing is read from the
  * process environment.  Returns 0, or -1 for an unknown name. */
 int topo_set_option(const char* name, int value);
+/* Measurement aid for bench.py: launches 148 x 8 CTAs of 8 independent DFMA chains x iters per thread on `stream`
+ * (scratch: DEVICE, 1 double, never written) and returns the float64 flops of the launch in *flops (HOST); timed by
+ * the caller with CUDA events = the FP64 pipe rate the wide Gaussian is compared with. */
+int topo_probe_dfma(int iters, double* scratch, double* flops, void* stream);
 
 /* ---- DEM statistics (one pass, cached by the host per uploaded DEM) ------------------------ */
 /* out_stats (DEVICE, 8 doubles): [0] min [1] max [2] #non-finite [3] #non-integer-valued
@@ -211,13 +215,17 @@ int topo_sx_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int
  * bank_cols (DEVICE): for column j of angle a, at int index 2 * (c0 + j): (lo, n) -- the rows lo .. lo+n-1
  * of that kernel column are walked, lo and n multiples of 4, lo + n <= hp, every weight outside
  * [lo, lo + n - 4] exactly zero (the corners of a rotated kernel: ~37% of the bounding boxes).
- * dir receives the angle index (degrees, angles are 0..n_angles-1). */
+ * dir receives the angle index (degrees, angles are 0..n_angles-1).
+ * Flat lists longer than 4 (the reference accepts any length, topo.py:389-396): the host packs the channels in
+ * banks of <= 4 and calls once per bank with group_flags bit 0 = "norm / dir hold the raw running (max, argmax) of
+ * the previous banks" and bit 1 = "leave them raw for the next bank" (0 for a single bank); ties between banks
+ * resolve to the lower angle, which is the reference's strict '>' over the angles in order. */
 int topo_zscore_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int rows, int nx,
                     float mean, float std, void* stream);
 int topo_valley_ridge_f32(const float* dem_norm, int64_t ld_in, float* norm, float* dir, int64_t ld_out,
                           const topo_view* v, const float* bank, const int* bank_hw,
                           const int64_t* bank_off, const int* bank_cols, int n_angles, int n_ch,
-                          int hmax, int wmax, void* stream);
+                          int hmax, int wmax, int group_flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,7 @@
-"""Import the UNMODIFIED reference from /root/reference  --  TEST INFRASTRUCTURE ONLY.
+"""Import the UNMODIFIED reference  --  TEST / BENCH INFRASTRUCTURE ONLY.
 
-Works only in the authoring container (the GPU box has no /root/reference).  Four stub packages
+From /root/reference in the authoring container; on the GPU box (no /root/reference) from the byte-for-byte staged
+archive ``oracle/_ref/topo_descriptors_ref.zip`` made by ``oracle/build_ref.py`` (git-ignored, shipped by gpurun).  Four stub packages
 under ``oracle/_stubs`` stand in for the reference's missing imports (xarray, dask, utm,
 yaconfigobject).  Used by ``oracle/make_golden.py`` to generate the golden
 vectors in ``tests/golden`` and by ``tests/test_oracle.py`` (skipped when the reference is absent).
@@ -12,12 +13,23 @@ import warnings
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_stubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STUBS = os.path.join(_HERE, "_stubs")
+
+
+def _root():
+    """sys.path entry that provides ``topo_descriptors``: the reference tree, or the staged archive (zipimport)."""
+    if os.path.isdir("/root/reference/topo_descriptors"):
+        return "/root/reference"
+    staged = os.path.join(_HERE, "_ref", "topo_descriptors_ref.zip")
+    return staged if os.path.isfile(staged) else None
+
+
+REFERENCE_ROOT = _root()
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "topo_descriptors"))
+    return REFERENCE_ROOT is not None
 
 
 def load():

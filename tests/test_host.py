@@ -320,8 +320,8 @@ def test_c_abi_argument_errors_are_reported_before_any_launch():
           match="n_az")
     fails("topo_sx_f32", fake, 64, fake, 64, 64 * 48, vp, fake, fake, fake, 1, 3, ctypes.c_float(10.0), -4, 3, -3, 3, null,
           match="exceed the window")
-    fails("topo_valley_ridge_f32", fake, 64, fake, fake, 64, vp, fake, fake, fake, fake, 180, 5, 9, 9, null,
-          match="flat_list of length 5")
+    fails("topo_valley_ridge_f32", fake, 64, fake, fake, 64, vp, fake, fake, fake, fake, 180, 5, 9, 9, 0, null,
+          match="5 channels in one bank")
     fails("topo_fill_na_f32", fake, 64, fake, 64, 48, 200000, null, 0, ctypes.c_float(0.0), null, null, match="")
     # size 1: kernel sum - 1 == 0 in the reference; handled by the fill entry point, which needs a real buffer -> not called here
     assert _lib.load().topo_last_error()

@@ -127,11 +127,13 @@ def mix_channels(kernels_rot):
     return out.astype(np.float32)
 
 
-def build_valley_bank(size, mode, flat_list, angles=None):
+def build_valley_bank(size, mode, flat_list, angles=None, rotate=None):
     """Pack the 180-angle bank for ``topo_valley_ridge_f32`` (layout in include/topo_b200.h):
     per angle a [w][hp][4] float32 block of the channel-mixed kernels, flipped in both axes so the
     device correlates, rows h..hp-1 zero; plus, per kernel column, the 4-aligned row range (lo, n) outside
-    which every weight is exactly zero (the corners of the rotated bounding box), so the device skips them."""
+    which every weight is exactly zero (the corners of the rotated bounding box), so the device skips them.
+    Flat lists longer than 4: ``"groups"`` holds one such bank per 4 mixed channels (the device keeps one running
+    maximum across them).  ``rotate``: callable(kernels, angle) replacing :func:`rotate_kernels` (the device rotation)."""
     if mode not in ("valley", "ridge"):
         raise ValueError(f"Unknown mode {mode!r}")
     flat_list = list(flat_list)
@@ -140,11 +142,20 @@ def build_valley_bank(size, mode, flat_list, angles=None):
         base = base * np.float32(-1)
     if angles is None:
         angles = np.arange(0, 180, dtype=np.float32)
-    n_ch = base.shape[0]
+    rotate = rotate_kernels if rotate is None else rotate
+    mixed_all = [mix_channels(rotate(base, ang)) for ang in angles]
+    if base.shape[0] > 4:
+        groups = [_pack_bank([m[c : c + 4] for m in mixed_all]) for c in range(0, base.shape[0], 4)]
+        return {"groups": groups, "n_angles": len(mixed_all), "n_ch": base.shape[0],
+                "hmax": max(g["hmax"] for g in groups), "wmax": max(g["wmax"] for g in groups)}
+    return _pack_bank(mixed_all)
+
+
+def _pack_bank(mixed_all):
+    n_ch = mixed_all[0].shape[0]
     blocks, hw, off, cols = [], [], [], []
     pos = 0
-    for ang in angles:
-        mixed = mix_channels(rotate_kernels(base, ang))
+    for mixed in mixed_all:
         flipped = mixed[:, ::-1, ::-1]
         F, h, w = flipped.shape
         hp = 4 * ((h + 3 + 3) // 4)

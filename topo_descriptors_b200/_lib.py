@@ -46,6 +46,7 @@ PROTOTYPES = {
     "topo_last_error": (c_char_p, []),
     "topo_launch_count": (c_longlong, []),
     "topo_set_option": (c_int, [c_char_p, c_int]),
+    "topo_probe_dfma": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
     "topo_profile_enable": (c_int, [c_int]),
     "topo_profile_dump": (c_int, [c_char_p, c_size_t]),
     "topo_dem_stats_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -75,7 +76,7 @@ PROTOTYPES = {
                                      c_void_p, c_void_p]),
     "topo_zscore_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_float, c_void_p]),
     "topo_valley_ridge_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, _VP, c_void_p, c_void_p,
-                                      c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+                                      c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _LIB = None

@@ -400,6 +400,23 @@ __global__ void __launch_bounds__(256) gradient_kernel(const GradParams p, int v
     }
 }
 
+// The weight table of the column kernel lives in shared memory: 8 B per tap.  Up to 48 KB (radius 3064) without
+// ceremony, beyond that (the reference's own example goes to 100 km = radius 4001 on a 25 m grid) the kernel opts in
+// to the full 227 KB (radius ~14 500; one CTA per SM from 113 KB on).
+static int axis0_smem_opt_in(size_t smem, int lw) {
+    TOPO_CHECK(smem <= 227 * 1024, "gaussian radius %d too large (the weight table must fit 227 KB of shared memory)", lw);
+    if (smem <= 48 * 1024) return 0;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    TOPO_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        TOPO_CUDA(cudaFuncSetAttribute(gauss_axis0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TOPO_CUDA(cudaFuncSetAttribute(gauss_axis0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    return 0;
+}
+
 static int check_rows_reflect(const topo_view* v, int lo_off, int hi_off, const char* what) {
     // rows out_gy0+lo_off .. out_gy0+out_rows-1+hi_off, reflected into the image, must be in the band
     const int a = v->out_gy0 + lo_off, b = v->out_gy0 + v->out_rows - 1 + hi_off;
@@ -467,7 +484,7 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
         GaussParams p{cur, dst, cur_ld, dst_ld, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_y, lw_y};
         dim3 grid(ceil_div(v->nx, kA0Cols), ceil_div(v->out_rows, 8 * kK));
         const size_t smem = (size_t)gauss_steps(lw_y) * sizeof(double);
-        TOPO_CHECK(smem <= 48 * 1024, "gaussian radius %d too large", lw_y);
+        if (axis0_smem_opt_in(smem, lw_y)) return -1;
         if (nan_safe)
             TOPO_LAUNCH("gauss_axis0<nansafe>", s, gauss_axis0_kernel<true><<<grid, dim3(32, 8), smem, s>>>(p));
         else
@@ -492,7 +509,7 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
         GaussParams p{t1, t2, tpitch, tpitch, v->out_rows, v->nx, 0, v->nx, 0, v->nx, w_x, lw_x};
         dim3 grid(ceil_div(v->out_rows, kA0Cols), ceil_div(v->nx, 8 * kK));
         const size_t smem = (size_t)gauss_steps(lw_x) * sizeof(double);
-        TOPO_CHECK(smem <= 48 * 1024, "gaussian radius %d too large", lw_x);
+        if (axis0_smem_opt_in(smem, lw_x)) return -1;
         if (nan_safe)
             TOPO_LAUNCH("gauss_axis0<nansafe>", s, gauss_axis0_kernel<true><<<grid, dim3(32, 8), smem, s>>>(p));
         else

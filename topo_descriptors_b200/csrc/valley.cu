@@ -40,6 +40,8 @@ struct ValleyParams {
     int n_angles;
     int HT, HB, HL, HR;  // halos: max anchor / max (h-1-anchor) over the angles
     int tile_pitch;
+    int resume;  // flat lists longer than 4 run in channel groups: start from the raw (max, argmax) already in norm / dir
+    int raw;     // ... and leave them raw (no clip) for the next group
 };
 
 template <int NCH, bool SMEM>
@@ -72,6 +74,20 @@ __global__ void __launch_bounds__(256) valley_kernel(const ValleyParams p) {
     for (int c = 0; c < kVC; ++c)
 #pragma unroll
         for (int q = 0; q < kVQ; ++q) best[c][q] = -INFINITY, bdir[c][q] = 0.f;
+    if (p.resume) {
+#pragma unroll
+        for (int c = 0; c < kVC; ++c) {
+            const int x = x0 + tx + 32 * c;
+#pragma unroll
+            for (int q = 0; q < kVQ; ++q) {
+                const int gy = y0 + ty * kVQ + q;
+                if (x < p.nx && gy < p.out_gy0 + p.out_rows) {
+                    const int64_t o = (int64_t)(gy - p.out_gy0) * p.ld_out + x;
+                    best[c][q] = p.norm[o], bdir[c][q] = p.dir[o];
+                }
+            }
+        }
+    }
 
     for (int a = 0; a < p.n_angles; ++a) {
         const int h = p.bank_hw[4 * a], w = p.bank_hw[4 * a + 1], hp = p.bank_hw[4 * a + 2];
@@ -134,7 +150,9 @@ __global__ void __launch_bounds__(256) valley_kernel(const ValleyParams p) {
                 float m = acc[c][q][0];
 #pragma unroll
                 for (int ch = 1; ch < NCH; ++ch) m = fmaxf(m, acc[c][q][ch]);
-                if (m > best[c][q]) best[c][q] = m, bdir[c][q] = (float)a;
+                // strict '>' over the angles in order = the first angle that reaches the maximum; written so that it
+                // also holds when a later channel group revisits earlier angles
+                if (m > best[c][q] || (m == best[c][q] && (float)a < bdir[c][q])) best[c][q] = m, bdir[c][q] = (float)a;
             }
     }
 
@@ -147,7 +165,7 @@ __global__ void __launch_bounds__(256) valley_kernel(const ValleyParams p) {
             const int gy = y0 + ty * kVQ + q;
             if (gy < p.out_gy0 + p.out_rows) {
                 const int64_t o = (int64_t)(gy - p.out_gy0) * p.ld_out + x;
-                p.norm[o] = fmaxf(best[c][q], 0.f);
+                p.norm[o] = p.raw ? best[c][q] : fmaxf(best[c][q], 0.f);
                 p.dir[o] = bdir[c][q];
             }
         }
@@ -162,11 +180,12 @@ extern "C" {
 
 int topo_valley_ridge_f32(const float* dem_norm, int64_t ld_in, float* norm, float* dir, int64_t ld_out,
                           const topo_view* v, const float* bank, const int* bank_hw, const int64_t* bank_off,
-                          const int* bank_cols, int n_angles, int n_ch, int hmax, int wmax, void* stream) {
+                          const int* bank_cols, int n_angles, int n_ch, int hmax, int wmax, int group_flags, void* stream) {
     TOPO_CHECK(dem_norm && norm && dir && bank && bank_hw && bank_off && bank_cols, "null pointer");
     if (validate_view(v)) return -1;
     TOPO_CHECK(n_angles >= 1, "no angles");
-    TOPO_CHECK(n_ch >= 1 && n_ch <= 4, "flat_list of length %d is not supported (1..4)", n_ch);
+    TOPO_CHECK(n_ch >= 1 && n_ch <= 4, "%d channels in one bank (1..4; longer flat lists run in groups, see topo_b200.h)", n_ch);
+    TOPO_CHECK(group_flags >= 0 && group_flags <= 3, "bad group_flags");
     TOPO_CHECK(hmax >= 1 && wmax >= 1, "bad kernel extents");
     if (v->out_rows == 0) return 0;
     ValleyParams p;
@@ -175,6 +194,7 @@ int topo_valley_ridge_f32(const float* dem_norm, int64_t ld_in, float* norm, flo
     p.out_gy0 = v->out_gy0, p.out_rows = v->out_rows;
     p.bank = bank, p.bank_hw = bank_hw, p.bank_off = bank_off, p.n_angles = n_angles;
     p.bank_cols = reinterpret_cast<const int2*>(bank_cols);
+    p.resume = group_flags & 1, p.raw = (group_flags >> 1) & 1;
     // anchors are h/2, w/2: rows above <= hmax/2; rows below h - 1 - h/2 <= h/2 <= hmax/2 for every h
     p.HT = hmax / 2, p.HB = hmax / 2;
     p.HL = wmax / 2, p.HR = wmax / 2;

@@ -407,12 +407,16 @@ def zscore(dem, mean, sd):
 
 
 def valley_ridge(dem_norm, bank, out_gy0=None, out_rows=None):
-    """Running (max, argmax) over the rotated-kernel bank -> (norm, dir) tensors."""
+    """Running (max, argmax) over the rotated-kernel bank -> (norm, dir) tensors.  ``bank``: one packed bank, or a dict
+    whose ``"groups"`` lists several (flat lists longer than 4 run in groups of 4 channels sharing the running maximum)."""
     require_cuda()
     v = dem_norm.view(out_gy0, out_rows)
     norm = _new(v.out_rows, dem_norm.nx, dem_norm.tensor)
     direction = _new(v.out_rows, dem_norm.nx, dem_norm.tensor)
-    _lib.call("topo_valley_ridge_f32", _ptr(dem_norm.tensor), dem_norm.ld, _ptr(norm), _ptr(direction),
-              int(norm.stride(0)), ctypes.byref(v), _ptr(bank["data"]), _ptr(bank["hw"]), _ptr(bank["off"]),
-              _ptr(bank["cols"]), int(bank["n_angles"]), int(bank["n_ch"]), int(bank["hmax"]), int(bank["wmax"]), _stream())
+    groups = bank["groups"] if "groups" in bank else [bank]
+    for g, b in enumerate(groups):
+        flags = (1 if g > 0 else 0) | (2 if g + 1 < len(groups) else 0)
+        _lib.call("topo_valley_ridge_f32", _ptr(dem_norm.tensor), dem_norm.ld, _ptr(norm), _ptr(direction),
+                  int(norm.stride(0)), ctypes.byref(v), _ptr(b["data"]), _ptr(b["hw"]), _ptr(b["off"]),
+                  _ptr(b["cols"]), int(b["n_angles"]), int(b["n_ch"]), int(b["hmax"]), int(b["wmax"]), flags, _stream())
     return norm, direction

@@ -237,11 +237,14 @@ def _device_bank(size, mode, flat_list, device):
         import torch
 
         host = geo.build_valley_bank(int(size), mode, flat_list)
-        bank = dict(host)
-        bank["data"] = torch.from_numpy(host["data"]).to(device)
-        bank["hw"] = torch.from_numpy(host["hw"]).to(device)
-        bank["off"] = torch.from_numpy(host["off"]).to(device)
-        bank["cols"] = torch.from_numpy(host["cols"]).to(device)
+
+        def upload(h):
+            b = dict(h)
+            for k in ("data", "hw", "off", "cols"):
+                b[k] = torch.from_numpy(h[k]).to(device)
+            return b
+
+        bank = dict(host, groups=[upload(g) for g in host["groups"]]) if "groups" in host else upload(host)
         if len(_BANK_CACHE) > 16:
             _BANK_CACHE.clear()
         _BANK_CACHE[key] = bank
