@@ -134,10 +134,13 @@ int topo_nan_indices_f32(const float* dem, int64_t ld_in, int rows, int nx, int 
  * 16-bit halves: one more gather pass, same exact result. */
 size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what /*0 tpi, 1 std*/, int all_integer,
                                  double zmin, double zmax,
-                                 int cache_max_size /* max_size of the topo_disc_cache that will be passed, else 0 */);
-/* tpi(size) and std(size) of an integer-valued DEM both need the disc sums of trunc(z): when this returns 1
- * the first call can keep them (tsum_op = 1, tsum = out_rows*nx uint64 on the DEVICE) and the second reuse
- * them (tsum_op = 2), which removes one of the three gather passes of a tpi+std pair.  tsum_op = 0: off. */
+                                 int cache_max_size /* max_size of the topo_disc_cache that will be passed, else 0 */,
+                                 int tsum_op /* the tsum_op the call will pass */);
+/* tpi(size) and std(size) of one DEM share raw plane sums: trunc(z) - tmin for integer-valued DEMs (returns 1), and
+ * for float DEMs also the fraction plane (returns 2; tpi then runs as the exact two-plane TPI_X rather than the
+ * one-plane quantised TPI_Q, so a tpi + std pair walks 3 planes instead of 4).  When the return value n is > 0 the
+ * first call can keep the sums (tsum_op = 1, tsum = n * out_rows * nx uint64 on the DEVICE) and the second reuse them
+ * (tsum_op = 2).  0: no sharing for this size / DEM; tsum_op = 0: off. */
 int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, double zmin, double zmax,
                           int cache_max_size /* 0: no plane cache */);
 /* 0: this DEM / size cannot share planes (the calls then run un-cached; pass cache = NULL). */
@@ -148,7 +151,7 @@ size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer, 
  * mask, 10 dynamic shared memory of the walk, 11 plane halo, 12 plane pitch, 13 plane rows, 14 workspace
  * bytes, 15 bytes of one cached plane region, 16 split square planes. */
 int topo_disc_plan_info(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax,
-                        int cache_max_size, long long* info);
+                        int cache_max_size, int tsum_op, long long* info);
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
                  int size, int all_integer, double zmin, double zmax, unsigned long long* tsum,
                  int tsum_op, topo_disc_cache* cache, void* ws, size_t ws_bytes, void* stream);

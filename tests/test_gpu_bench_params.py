@@ -98,11 +98,14 @@ def test_valley_ridge_size_41():
     z = fractal_dem(160, 192, seed=14)
     wn, wd, gap = O.valley_ridge_exact(z, 41, "valley", return_gap=True, direct_limit=0)
     norm, direction = topo.valley_ridge(z, 41, "valley")
-    assert maxdiff(norm, wn) <= 2e-3  # float32 sums of ~3000 products of magnitude ~1
-    decided = gap > 1e-2
+    # norm reaches ~2700 here (it grows with the kernel area) and is a float32 sum of ~3200 products per channel:
+    # the tolerance is relative, 6e-6 of the largest value = what SURVEY section 9 proposes (1e-3 at values ~170)
+    tol = max(TOL_M, 6e-6 * float(np.abs(wn).max()))
+    assert maxdiff(norm, wn) <= tol
+    decided = gap > 10 * tol
     assert decided.mean() > 0.5 and np.array_equal(direction[decided], wd[decided])
     rn, _ = topo.valley_ridge(z, 41, "ridge")
-    assert maxdiff(rn, O.valley_ridge_exact(z, 41, "ridge", direct_limit=0)[0]) <= 2e-3
+    assert maxdiff(rn, O.valley_ridge_exact(z, 41, "ridge", direct_limit=0)[0]) <= tol
 
 
 def test_valley_ridge_flat_list_longer_than_four():
@@ -154,3 +157,40 @@ def test_row_bands_equal_the_whole_image_under_torchrun():
            "--master-addr", "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "tests", "mgpu_check.py")]
     res = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-2000:]
+
+
+@pytest.mark.parametrize("sigma", [33.0, 40.0, 100.25, 300.0, (40.0, 2.0), (1.5, 150.0)])
+def test_gaussian_fft_path_matches_scipy_and_the_direct_taps(sigma):
+    """Radii >= 128 run as overlap-save float64 FFT passes (transform lengths 2048 / 4096 / 8192); the same call with
+    the switch off runs 2*lw+1 float64 taps per pixel.  Both must equal scipy's float32 output except rare one-ulp
+    flips, on an image that is not a multiple of anything and shorter than the widest kernel (multiple reflections)."""
+    from scipy import ndimage
+
+    from topo_descriptors_b200 import _lib
+
+    z = fractal_dem(1111, 1303, seed=18)
+    want = ndimage.gaussian_filter(z, sigma)
+    got = topo.dem(z, sigma)
+    _lib.set_option("gauss_fft", False)
+    try:
+        direct = topo.dem(z, sigma)
+    finally:
+        _lib.set_option("gauss_fft", True)
+    for name, arr in (("fft", got), ("direct", direct)):
+        bad = arr != want
+        assert bad.mean() <= 1e-3, f"{name}: {bad.mean():.2e} of the pixels differ from scipy"
+        assert np.all(np.abs(arr[bad] - want[bad]) <= np.spacing(np.abs(want[bad])) * 1.01), name
+    assert (got != direct).mean() <= 1e-3
+
+
+def test_gaussian_fft_on_a_row_band_is_bit_identical():
+    """The FFT pass works in global coordinates (reflection at the global edges, halo rows from the band)."""
+    z = fractal_dem(1500, 700, seed=19)
+    whole = DeviceDEM(dev.to_device(z))
+    sigma, lw = 50.25, 201
+    ref = dev.gauss(whole, sigma, sigma)
+    for lo, hi in ((0, 400), (400, 1100), (1100, 1500)):
+        a, b = max(0, lo - lw), min(1500, hi + lw)
+        band = DeviceDEM(whole.tensor[a:b].contiguous(), gny=1500, gy0=a, stats=whole.stats)
+        out = dev.gauss(band, sigma, sigma, lo, hi - lo)
+        assert bool((out == ref[lo:hi]).all()), (lo, hi)

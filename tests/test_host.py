@@ -284,15 +284,16 @@ def test_library_exports_every_declared_symbol():
     v = _lib.View(1440, 900, 0, 900, 0, 900)
     import ctypes
 
-    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 17, 0, 1, 200.0, 3400.0, 0) == 0  # fused: no workspace
-    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 801, 0, 1, 200.0, 3400.0, 0) > 4 * 900 * 1440
+    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 17, 0, 1, 200.0, 3400.0, 0, 0) == 0  # fused: no workspace
+    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 801, 0, 1, 200.0, 3400.0, 0, 0) > 4 * 900 * 1440
     # with a plane cache the planes live there: the workspace shrinks and mid sizes walk the cached planes
     rng = (200.0, 3400.0)
     assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) > 10 * 4 * 900 * 1440
     assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0, *rng) == 2 * lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng)
-    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 41, 1, 1, *rng, 801) >= 2 * 8 * 900 * 1440  # raw sums of two planes
+    assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 41, 1, 1, *rng, 801, 0) >= 2 * 8 * 900 * 1440  # raw sums of two planes
     assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, *rng, 0) == 0
     assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, *rng, 801) == 1
+    assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 0, *rng, 801) == 2  # float DEM: T and fraction planes
 
 
 def test_c_abi_argument_errors_are_reported_before_any_launch():
@@ -355,22 +356,23 @@ def test_disc_queries_agree_with_the_plan_over_a_size_x_range_grid():
                     if hint and size > hint:
                         continue
                     for what in (0, 1):
-                        assert lib.topo_disc_plan_info(vp, size, what, integer, zmin, zmax, hint, info) == 0, (
+                        assert lib.topo_disc_plan_info(vp, size, what, integer, zmin, zmax, hint, 0, info) == 0, (
                             size, what, integer, zmin, zmax, hint, lib.topo_last_error())
                         fused, cached, ws, off_partial = info[1], info[4], info[14], info[15]
                         need = 0 if fused else (ws - off_partial if cached else ws)
-                        got = lib.topo_disc_workspace_bytes(vp, size, what, integer, zmin, zmax, hint)
+                        got = lib.topo_disc_workspace_bytes(vp, size, what, integer, zmin, zmax, hint, 0)
                         assert got == need, (size, what, integer, zmin, zmax, hint, got, need)
                     if lib.topo_disc_shares_tsum(vp, size, integer, zmin, zmax, hint):
                         a = (ctypes.c_longlong * 32)()
                         b = (ctypes.c_longlong * 32)()
-                        lib.topo_disc_plan_info(vp, size, 0, integer, zmin, zmax, hint, a)
-                        lib.topo_disc_plan_info(vp, size, 1, integer, zmin, zmax, hint, b)
-                        assert (a[0], b[0], a[1], b[1]) == (4, 2, 0, 0)  # TPI_I + STD_I, both two-pass
+                        lib.topo_disc_plan_info(vp, size, 0, integer, zmin, zmax, hint, 1, a)
+                        lib.topo_disc_plan_info(vp, size, 1, integer, zmin, zmax, hint, 1, b)
+                        # TPI_I + STD_I (integer DEM) or TPI_X + STD_F (float DEM), both two-pass
+                        assert (a[0], b[0], a[1], b[1]) == ((4, 2, 0, 0) if integer else (1, 3, 0, 0))
     # the advisor's cases: std(801) on 200..4800 and std(2001) now plan (split squares) instead of raising
     for size in (801, 2001):
-        assert lib.topo_disc_plan_info(vp, size, 1, 1, 200.0, 4800.0, 0, info) == 0 and info[16] == 1
-    assert lib.topo_disc_plan_info(vp, 801, 1, 1, 200.0, 3400.0, 0, info) == 0 and info[16] == 0
+        assert lib.topo_disc_plan_info(vp, size, 1, 1, 200.0, 4800.0, 0, 0, info) == 0 and info[16] == 1
+    assert lib.topo_disc_plan_info(vp, 801, 1, 1, 200.0, 3400.0, 0, 0, info) == 0 and info[16] == 0
     # a cache laid out for a split square holds one more plane region
     base = lib.topo_disc_cache_bytes(vp, 801, 1, 200.0, 3400.0)
     assert base > 0 and lib.topo_disc_cache_bytes(vp, 801, 1, 0.0, 4800.0) * 2 == base * 3

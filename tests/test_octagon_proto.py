@@ -80,7 +80,7 @@ def test_cxx_planner_matches_the_prototype_for_every_odd_size():
     sizes = list(range(41, 1203, 2)) + [2001, 3001, 4095, 8191]
     for size in sizes:
         v = _lib.View(2048, 4096, 0, 4096, 0, 4096)
-        assert lib.topo_disc_plan_info(ctypes.byref(v), size, 0, 1, 0.0, 500.0, size, info) == 0, size
+        assert lib.topo_disc_plan_info(ctypes.byref(v), size, 0, 1, 0.0, 500.0, size, 0, info) == 0, size
         mode, fused, hybrid, tiny, cached, oct_, u, vv, ndiag, acc, smem = list(info)[:11]
         assert (mode, fused, hybrid, tiny, cached, oct_) == (4, 0, 1, 0, 1, 1), size
         m = size // 2
@@ -91,12 +91,12 @@ def test_cxx_planner_matches_the_prototype_for_every_odd_size():
         assert smem <= 200 * 1024 and info[11] == m
     # without a cache: the inscribed square; small sizes: fused / tiny; even sizes: plain row spans
     v = _lib.View(2048, 4096, 0, 4096, 0, 4096)
-    assert lib.topo_disc_plan_info(ctypes.byref(v), 801, 0, 1, 0.0, 500.0, 0, info) == 0
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 801, 0, 1, 0.0, 500.0, 0, 0, info) == 0
     assert (info[2], info[4], info[5], info[6]) == (1, 0, 0, int(400 / math.sqrt(2)))
-    assert lib.topo_disc_plan_info(ctypes.byref(v), 9, 0, 1, 0.0, 500.0, 801, info) == 0 and (info[1], info[3]) == (1, 1)
-    assert lib.topo_disc_plan_info(ctypes.byref(v), 21, 1, 1, 0.0, 500.0, 801, info) == 0 and (info[1], info[3]) == (1, 0)
-    assert lib.topo_disc_plan_info(ctypes.byref(v), 400, 0, 1, 0.0, 500.0, 801, info) == 0 and (info[1], info[2], info[4]) == (0, 0, 1)
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 9, 0, 1, 0.0, 500.0, 801, 0, info) == 0 and (info[1], info[3]) == (1, 1)
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 21, 1, 1, 0.0, 500.0, 801, 0, info) == 0 and (info[1], info[3]) == (1, 0)
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 400, 0, 1, 0.0, 500.0, 801, 0, info) == 0 and (info[1], info[2], info[4]) == (0, 0, 1)
     # float DEM: quantised plane with the scale of the sweep's largest size, or the exact two-plane mode for wide ranges
-    assert lib.topo_disc_plan_info(ctypes.byref(v), 201, 0, 0, 0.0, 3400.5, 801, info) == 0 and info[0] == 0 and info[4] == 1
-    assert lib.topo_disc_plan_info(ctypes.byref(v), 201, 0, 0, -2e5, 3e6, 801, info) == 0 and info[0] == 1
-    assert lib.topo_disc_plan_info(ctypes.byref(v), 201, 1, 0, 0.0, 3400.5, 801, info) == 0 and info[0] == 3
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 201, 0, 0, 0.0, 3400.5, 801, 0, info) == 0 and info[0] == 0 and info[4] == 1
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 201, 0, 0, -2e5, 3e6, 801, 0, info) == 0 and info[0] == 1
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 201, 1, 0, 0.0, 3400.5, 801, 0, info) == 0 and info[0] == 3

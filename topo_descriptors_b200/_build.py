@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libtopo_b200.so")
-SOURCES = ["core.cu", "disc.cu", "gauss.cu", "sx.cu", "valley.cu", "prestage.cu"]
+SOURCES = ["core.cu", "disc.cu", "gauss.cu", "gauss_fft.cu", "sx.cu", "valley.cu", "prestage.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

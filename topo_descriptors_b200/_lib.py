@@ -53,10 +53,10 @@ PROTOTYPES = {
     "topo_dem_stats_f32": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "topo_fill_f32": (c_int, [c_void_p, c_int, c_int, c_int64, c_float, c_void_p]),
     "topo_stamp_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
-    "topo_disc_workspace_bytes": (c_size_t, [_VP, c_int, c_int, c_int, c_double, c_double, c_int]),
+    "topo_disc_workspace_bytes": (c_size_t, [_VP, c_int, c_int, c_int, c_double, c_double, c_int, c_int]),
     "topo_disc_shares_tsum": (c_int, [_VP, c_int, c_int, c_double, c_double, c_int]),
     "topo_disc_cache_bytes": (c_size_t, [_VP, c_int, c_int, c_double, c_double]),
-    "topo_disc_plan_info": (c_int, [_VP, c_int, c_int, c_int, c_double, c_double, c_int, c_void_p]),
+    "topo_disc_plan_info": (c_int, [_VP, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p]),
     "topo_tpi_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_int, c_int, c_double, c_double,
                              c_void_p, c_int, _CP, c_void_p, c_size_t, c_void_p]),
     "topo_std_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, _VP, c_int, c_int, c_double, c_double,

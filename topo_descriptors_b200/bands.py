@@ -139,7 +139,7 @@ def sweep(core, ctx, sizes, sigmas, res_x, res_y, what=("tpi", "std", "gradient"
     ry, ry2d = res_y
     for i, size in enumerate(sizes):
         if "tpi" in what:
-            out = dev.tpi(ddem, size, ctx.r0, ctx.rows)
+            out = dev.tpi(ddem, size, ctx.r0, ctx.rows, pair_std="std" in what)
             calls += 1
             if sink:
                 sink("tpi", i, out)

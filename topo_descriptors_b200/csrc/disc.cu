@@ -93,6 +93,8 @@ struct DiscParams {
     unsigned long long* partial;  // two-pass, multi-plane modes: raw disc sums, [plane][out_rows][nx]
     int64_t partial_stride;
     unsigned long long* tsum;  // optional: raw sums of the T plane (trunc(z) - tmin), shared between tpi and std
+    unsigned long long* fsum;  // optional, float DEMs: raw sums of the fraction plane, shared likewise
+    int fplane;                // index of the fraction plane among this mode's planes (-1: none)
     int nrows;   // two-pass: rows of the prefix planes
     int64_t ld_in, ld_out;
     int64_t plane_stride;  // elements between consecutive plane copies
@@ -1197,7 +1199,9 @@ __global__ void __launch_bounds__(kThreads, HYBRID ? 3 : 1) disc_span_kernel(con
             }
         } else {
             const int64_t idx = (int64_t)(gy - p.out_gy0) * p.nx + x;
-            unsigned long long* o = (plane == 0 && p.tsum) ? p.tsum + idx : p.partial + plane * p.partial_stride + idx;
+            unsigned long long* o = (plane == 0 && p.tsum)          ? p.tsum + idx
+                                    : (plane == p.fplane && p.fsum) ? p.fsum + idx
+                                                                    : p.partial + plane * p.partial_stride + idx;
             o[0] = v0;
             if (x + 1 < p.nx) o[1] = v1;
         }
@@ -1213,7 +1217,8 @@ __global__ void __launch_bounds__(256) disc_finish_kernel(const DiscParams p) {
         const int r = (int)(idx / p.nx), x = (int)(idx - (int64_t)r * p.nx);
         unsigned long long acc[NARR];
 #pragma unroll
-        for (int a = 0; a < NARR; ++a) acc[a] = (a == 0 && p.tsum) ? p.tsum[idx] : p.partial[a * p.partial_stride + idx];
+        for (int a = 0; a < NARR; ++a)
+            acc[a] = (a == 0 && p.tsum) ? p.tsum[idx] : (a == p.fplane && p.fsum) ? p.fsum[idx] : p.partial[a * p.partial_stride + idx];
         if constexpr (MODE == STD_I || MODE == STD_F) {
             if (p.qsplit) acc[1] += p.partial[NARR * p.partial_stride + idx] << 16;
         }
@@ -1398,7 +1403,7 @@ constexpr double kU32 = 4294967295.0;
 // span_size: the disc size the fixed-point scales are laid out for -- `size` itself, or the largest size of a sweep
 // that shares its planes through a topo_disc_cache (then every size of the sweep sees the same planes).
 static int plan_disc_impl(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, DiscPlan& pl,
-                          int cache_size, int span_size) {
+                          int cache_size, int span_size, bool pair) {
     TOPO_CHECK(size >= 2 && size <= kMaxSize, "kernel size %d outside [2, %d]", size, kMaxSize);
     TOPO_CHECK(isfinite(zmin) && isfinite(zmax) && zmin <= zmax, "DEM range is not finite");
     const double n = (double)disc_count(size);
@@ -1421,7 +1426,7 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
         int S32 = ilog2_floor(kU32 / (n * range));
         if (S32 > 20) S32 = 20;
         if (S32 >= 13 && span_size == size) S = S32;  // (depends on the size: not for shared planes)
-        if (S >= 10) {
+        if (S >= 10 && !pair) {  // pair: tpi shares the T and fraction sums with a std of the same size (exact TPI_X)
             mode = TPI_Q;
             p.scale = (float)ldexp(1.0, S);
             p.c0i = (int)ldexp(c0, S);
@@ -1469,6 +1474,7 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
     if (plan_geometry(v, size, narr_of(mode) + qsplit, max_rb(mode), pl, plane_halo, qsplit != 0)) return -1;
     if (pl.fused) pl.cached = false;
     p.qsplit = qsplit;
+    p.fplane = mode == TPI_X ? 1 : mode == STD_F ? 2 : -1;
     pl.acc_qh = qsplit && n * vmax_qh < kU32;
     pl.qh_kind = all_integer ? 2 : 4;
     pl.tiny = false;
@@ -1496,11 +1502,11 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
 // planes (scales of the largest size); a size that runs fused anyway, or whose shared layout does not fit the 32-bit
 // span sums, gets its own plan.
 static int plan_disc(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, DiscPlan& pl,
-                     int cache_size = 0) {
+                     int cache_size = 0, bool pair = false) {
     if (cache_size >= size && size >= 2) {
-        if (plan_disc_impl(v, size, what, all_integer, zmin, zmax, pl, cache_size, cache_size) == 0 && !pl.fused) return 0;
+        if (plan_disc_impl(v, size, what, all_integer, zmin, zmax, pl, cache_size, cache_size, pair) == 0 && !pl.fused) return 0;
     }
-    return plan_disc_impl(v, size, what, all_integer, zmin, zmax, pl, 0, size);
+    return plan_disc_impl(v, size, what, all_integer, zmin, zmax, pl, 0, size, pair);
 }
 
 static const char* mode_name(int mode) {
@@ -1668,7 +1674,7 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo
             return 0;
         case TPI_X:
             if (!reuse && (rc = launch_plane<PL_T, -1>(pl, 0, a0, s, cache))) return rc;
-            if ((rc = launch_plane<PL_F, -1>(pl, 1, a1, s, cache))) return rc;
+            if (!(reuse && pl.p.fsum) && (rc = launch_plane<PL_F, -1>(pl, 1, a1, s, cache))) return rc;
             TOPO_LAUNCH("disc_finish<TPI_X>", s, disc_finish_kernel<TPI_X><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
         case STD_I:
@@ -1689,7 +1695,7 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo
             } else if ((rc = launch_plane<PL_Q, -1>(pl, 1, a1, s, cache))) {
                 return rc;
             }
-            if ((rc = launch_plane<PL_F, -1>(pl, 2, a2, s, cache))) return rc;
+            if (!(reuse && pl.p.fsum) && (rc = launch_plane<PL_F, -1>(pl, 2, a2, s, cache))) return rc;
             TOPO_LAUNCH("disc_finish<STD_F>", s, disc_finish_kernel<STD_F><<<kNumSMs * 8, 256, 0, s>>>(pl.p));
             return 0;
     }
@@ -1708,7 +1714,7 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
     }
     DiscPlan pl;
     if (cache && !cache->mem) cache = nullptr;
-    if (plan_disc(v, size, what, all_integer, zmin, zmax, pl, cache ? cache->max_size : 0)) return -1;
+    if (plan_disc(v, size, what, all_integer, zmin, zmax, pl, cache ? cache->max_size : 0, tsum_op != 0)) return -1;
     if (!pl.cached) cache = nullptr;
     if (check_band(v, pl.p.halo)) return -1;
     pl.p.dem = dem, pl.p.out = out, pl.p.ld_in = ld_in, pl.p.ld_out = ld_out;
@@ -1735,6 +1741,8 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
             TOPO_CHECK(tsum != nullptr, "tsum_op %d needs a T-plane sum buffer", tsum_op);
             TOPO_CHECK(pl.mode != TPI_Q, "this size/DEM does not use the T plane (see topo_disc_shares_tsum)");
             pl.p.tsum = tsum;
+            // float DEMs keep the fraction-plane sums right behind the T-plane sums (topo_disc_shares_tsum == 2)
+            if (!all_integer) pl.p.fsum = tsum + (int64_t)v->out_rows * v->nx;
         }
         return launch_two_pass(pl, tsum_op, s, cache);
     }
@@ -1766,28 +1774,32 @@ extern "C" {
 // The three queries below make the SAME plan as run_disc (same range, integrality and cache size), so what they
 // report is what the call will do -- including its fall-back to an un-cached plan when the shared layout overflows.
 static bool quiet_plan(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, int cache_max_size,
-                       DiscPlan& pl) {
+                       DiscPlan& pl, bool pair = false) {
     if (!v || size < 2 || size > kMaxSize || validate_view(v)) return false;
     memset(&pl, 0, sizeof(pl));
-    return plan_disc(v, size, what, all_integer, zmin, zmax, pl, cache_max_size) == 0;
+    return plan_disc(v, size, what, all_integer, zmin, zmax, pl, cache_max_size, pair) == 0;
 }
 
 size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax,
-                                 int cache_max_size) {
+                                 int cache_max_size, int tsum_op) {
     DiscPlan pl;
-    if (!quiet_plan(v, size, what, all_integer, zmin, zmax, cache_max_size, pl)) return 0;
+    if (!quiet_plan(v, size, what, all_integer, zmin, zmax, cache_max_size, pl, tsum_op != 0)) return 0;
     if (pl.fused) return 0;
     // with a plane cache the planes live there and the workspace only holds the raw plane sums
     return pl.cached ? pl.ws_bytes - pl.off_partial : pl.ws_bytes;
 }
 
 int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, double zmin, double zmax, int cache_max_size) {
-    // tpi and std of the same size both run two-pass on the integer planes => std can reuse tpi's T-plane sums
-    if (!all_integer) return 0;
+    // tpi and std of the same size both run two-pass on the same planes => std can reuse tpi's raw plane sums:
+    // the T plane of integer-valued DEMs (returns 1), the T and fraction planes of float DEMs (returns 2: tpi then
+    // runs as the exact two-plane TPI_X instead of the one-plane quantised TPI_Q -- 3 gather passes per pair, not 4)
     DiscPlan a, b;
-    if (!quiet_plan(v, size, 0, all_integer, zmin, zmax, cache_max_size, a)) return 0;
-    if (!quiet_plan(v, size, 1, all_integer, zmin, zmax, cache_max_size, b)) return 0;
-    return (!a.fused && !b.fused && a.mode == TPI_I && b.mode == STD_I && a.p.tmin == b.p.tmin) ? 1 : 0;
+    if (!quiet_plan(v, size, 0, all_integer, zmin, zmax, cache_max_size, a, true)) return 0;
+    if (!quiet_plan(v, size, 1, all_integer, zmin, zmax, cache_max_size, b, true)) return 0;
+    if (a.fused || b.fused || a.p.tmin != b.p.tmin) return 0;
+    if (a.mode == TPI_I && b.mode == STD_I) return 1;
+    if (a.mode == TPI_X && b.mode == STD_F && a.p.fscale == b.p.fscale) return 2;
+    return 0;
 }
 
 size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer, double zmin, double zmax) {
@@ -1800,13 +1812,13 @@ size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer, 
 }
 
 int topo_disc_plan_info(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax,
-                        int cache_max_size, long long* info) {
+                        int cache_max_size, int tsum_op, long long* info) {
     // host-only introspection of the plan run_disc would execute (no launch, no GPU needed): used by the CPU tests
     TOPO_CHECK(info != nullptr, "null pointer");
     if (validate_view(v)) return -1;
     DiscPlan pl;
     memset(&pl, 0, sizeof(pl));
-    if (plan_disc(v, size, what, all_integer, zmin, zmax, pl, cache_max_size)) return -1;
+    if (plan_disc(v, size, what, all_integer, zmin, zmax, pl, cache_max_size, tsum_op != 0)) return -1;
     info[0] = pl.mode, info[1] = pl.fused, info[2] = pl.hybrid, info[3] = pl.tiny, info[4] = pl.cached;
     info[5] = pl.p.oct, info[6] = pl.p.asq, info[7] = pl.p.oct_v, info[8] = pl.p.oct_ndiag, info[9] = pl.acc;
     info[10] = (long long)pl.smem, info[11] = pl.p.halo, info[12] = pl.p.pitch, info[13] = pl.prefix_rows;

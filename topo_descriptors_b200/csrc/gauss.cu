@@ -16,6 +16,13 @@
 
 namespace topo {
 
+// gauss_fft.cu: overlap-save float64 FFT pass along the contiguous axis (wide radii)
+int fft_conv_length(int lw);
+size_t fft_conv_table_bytes(int lw);
+int fft_conv_rows(const float* in, int64_t ld_in, float* out, int64_t ld_out, int n_lines, int n_glob, int in0, int in_len,
+                  int out0, int out_len, const double* w, int lw, void* tables, cudaStream_t s);
+
+constexpr int kFftMinRadius = 128;  // from here the FFT pass beats 2*lw+1 float64 taps per pixel
 constexpr int kK = 16;  // outputs per thread along the filter axis (micro-benchmark: 41 DFMA/clk/SM vs 28 at K = 8)
 constexpr int kAxis1SmemMaxRadius = 64;  // wider axis-1 filters go through a transpose
 
@@ -402,16 +409,17 @@ __global__ void __launch_bounds__(256) gradient_kernel(const GradParams p, int v
 
 // The weight table of the column kernel lives in shared memory: 8 B per tap.  Up to 48 KB (radius 3064) without
 // ceremony, beyond that (the reference's own example goes to 100 km = radius 4001 on a 25 m grid) the kernel opts in
-// to the full 227 KB (radius ~14 500; one CTA per SM from 113 KB on).
+// to 224 KB (radius ~14 300; one CTA per SM from 113 KB on).
 static int axis0_smem_opt_in(size_t smem, int lw) {
-    TOPO_CHECK(smem <= 227 * 1024, "gaussian radius %d too large (the weight table must fit 227 KB of shared memory)", lw);
+    constexpr int kMax = 224 * 1024;  // 227 KB per CTA minus the kernel's static shared memory
+    TOPO_CHECK(smem <= (size_t)kMax, "gaussian radius %d too large (the weight table must fit 224 KB of shared memory)", lw);
     if (smem <= 48 * 1024) return 0;
     static bool attr_set[64] = {false};
     int dev = 0;
     TOPO_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        TOPO_CUDA(cudaFuncSetAttribute(gauss_axis0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        TOPO_CUDA(cudaFuncSetAttribute(gauss_axis0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TOPO_CUDA(cudaFuncSetAttribute(gauss_axis0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
+        TOPO_CUDA(cudaFuncSetAttribute(gauss_axis0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax));
         if (dev < 64) attr_set[dev] = true;
     }
     return 0;
@@ -438,6 +446,45 @@ static int check_rows_reflect(const topo_view* v, int lo_off, int hi_off, const 
     return 0;
 }
 
+// Which passes take the FFT route.  NaN-exact smoothing stays on the direct kernels: a transform would spread a
+// non-finite sample over its whole segment instead of scipy's +-lw.
+static bool fft_radius(int lw) { return lw >= kFftMinRadius && fft_conv_length(lw) > 0 && option_enabled(kOptGaussFft); }
+
+struct GaussWs {
+    size_t tmp;       // axis-0 result, out_rows x pitch (when both axes run)
+    size_t t1, t2;    // transposed planes
+    size_t tables;    // FFT twiddles + multipliers (one set, reused by the two axes)
+    size_t total;
+};
+
+static GaussWs gauss_ws_layout(const topo_view* v, int lw_y, int lw_x, bool do_y, bool do_x, bool allow_fft) {
+    auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t rows = (size_t)(v->out_rows > 0 ? v->out_rows : 1), in_rows = (size_t)v->in_rows;
+    const size_t pitch = ((size_t)v->nx + 3) & ~(size_t)3;
+    const bool fy = allow_fft && do_y && fft_radius(lw_y), fx = allow_fft && do_x && fft_radius(lw_x);
+    GaussWs w{};
+    size_t off = 0;
+    w.tmp = off;
+    if (do_y && do_x) off = align(off + pitch * rows * sizeof(float));
+    // transposed planes: FFT axis 0 needs (nx x in_rows) and (nx x out_rows); the direct wide axis-1 route needs
+    // (nx x out_rows) twice
+    const size_t tp_in = ((in_rows + 3) & ~(size_t)3), tp_out = ((rows + 3) & ~(size_t)3);
+    size_t n1 = 0, n2 = 0;
+    if (fy) n1 = tp_in * v->nx, n2 = tp_out * v->nx;
+    if (do_x && !fx && lw_x > kAxis1SmemMaxRadius) n1 = n1 > tp_out * v->nx ? n1 : tp_out * v->nx, n2 = n2 > tp_out * v->nx ? n2 : tp_out * v->nx;
+    w.t1 = off;
+    off = align(off + n1 * sizeof(float));
+    w.t2 = off;
+    off = align(off + n2 * sizeof(float));
+    w.tables = off;
+    size_t tb = 0;
+    if (fy) tb = fft_conv_table_bytes(lw_y);
+    if (fx && fft_conv_table_bytes(lw_x) > tb) tb = fft_conv_table_bytes(lw_x);
+    off = align(off + tb);
+    w.total = off;
+    return w;
+}
+
 }  // namespace topo
 
 using namespace topo;
@@ -446,14 +493,10 @@ extern "C" {
 
 size_t topo_gauss_workspace_bytes(const topo_view* v, int lw_y, int lw_x) {
     if (!v) return 0;
-    (void)lw_y;
-    const size_t rows = (size_t)(v->out_rows > 0 ? v->out_rows : 1);
-    // axis-0 result for the output rows (pitch = nx rounded to 4) ...
-    const size_t pitch = ((size_t)v->nx + 3) & ~(size_t)3;
-    size_t bytes = pitch * rows * sizeof(float);
-    // ... plus two transposed planes when the axis-1 radius takes the transpose route
-    if (lw_x > kAxis1SmemMaxRadius) bytes += 2 * ((rows + 3) & ~(size_t)3) * (size_t)v->nx * sizeof(float);
-    return bytes;
+    // the route depends on nan_safe, which the query does not know: room for either
+    const size_t a = gauss_ws_layout(v, lw_y, lw_x, lw_y >= 0, lw_x >= 0, true).total;
+    const size_t b = gauss_ws_layout(v, lw_y, lw_x, lw_y >= 0, lw_x >= 0, false).total;
+    return a > b ? a : b;
 }
 
 int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,
@@ -467,46 +510,57 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
     cudaStream_t s = (cudaStream_t)stream;
     const bool do_y = w_y != nullptr, do_x = w_x != nullptr;
     TOPO_CHECK(in != out, "in-place smoothing is not supported");
+    const GaussWs L = gauss_ws_layout(v, lw_y, lw_x, do_y, do_x, !nan_safe);
+    TOPO_CHECK(L.total == 0 || (ws && ws_bytes >= L.total), "workspace too small: need %zu bytes, got %zu", L.total, ws_bytes);
+    TOPO_CHECK(L.total == 0 || (reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
+    unsigned char* wsb = reinterpret_cast<unsigned char*>(ws);
+    const bool fy = !nan_safe && do_y && fft_radius(lw_y), fx = !nan_safe && do_x && fft_radius(lw_x);
+    const int64_t pitch = ((int64_t)v->nx + 3) & ~(int64_t)3;
+    const int64_t tp_in = ((int64_t)v->in_rows + 3) & ~(int64_t)3, tp_out = ((int64_t)v->out_rows + 3) & ~(int64_t)3;
 
     const float* cur = in;
     int64_t cur_ld = ld_in;
     int cur_gy0 = v->in_gy0, cur_rows = v->in_rows;
     if (do_y) {
         if (check_rows_reflect(v, -lw_y, lw_y, "gaussian axis 0")) return -1;
-        float* dst = out;
-        int64_t dst_ld = ld_out;
-        if (do_x) {
-            const int64_t pitch = ((int64_t)v->nx + 3) & ~(int64_t)3;
-            TOPO_CHECK(ws && ws_bytes >= (size_t)pitch * v->out_rows * sizeof(float), "workspace too small");
-            dst = (float*)ws;
-            dst_ld = pitch;
+        float* dst = do_x ? reinterpret_cast<float*>(wsb + L.tmp) : out;
+        const int64_t dst_ld = do_x ? pitch : ld_out;
+        if (fy) {
+            // transpose the band, filter its lines (= the image columns) with the FFT pass, transpose back
+            float* t1 = reinterpret_cast<float*>(wsb + L.t1);
+            float* t2 = reinterpret_cast<float*>(wsb + L.t2);
+            dim3 tg(ceil_div(v->nx, 32), ceil_div(v->in_rows, 32));
+            TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(in, ld_in, t1, tp_in, v->in_rows, v->nx));
+            if (fft_conv_rows(t1, tp_in, t2, tp_out, v->nx, v->gny, v->in_gy0, v->in_rows, v->out_gy0, v->out_rows, w_y, lw_y,
+                              wsb + L.tables, s))
+                return -1;
+            dim3 tg2(ceil_div(v->out_rows, 32), ceil_div(v->nx, 32));
+            TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg2, dim3(32, 8), 0, s>>>(t2, tp_out, dst, dst_ld, v->nx, v->out_rows));
+        } else {
+            GaussParams p{cur, dst, cur_ld, dst_ld, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_y, lw_y};
+            dim3 grid(ceil_div(v->nx, kA0Cols), ceil_div(v->out_rows, 8 * kK));
+            const size_t smem = (size_t)gauss_steps(lw_y) * sizeof(double);
+            if (axis0_smem_opt_in(smem, lw_y)) return -1;
+            if (nan_safe)
+                TOPO_LAUNCH("gauss_axis0<nansafe>", s, gauss_axis0_kernel<true><<<grid, dim3(32, 8), smem, s>>>(p));
+            else
+                TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<false><<<grid, dim3(32, 8), smem, s>>>(p));
         }
-        GaussParams p{cur, dst, cur_ld, dst_ld, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_y, lw_y};
-        dim3 grid(ceil_div(v->nx, kA0Cols), ceil_div(v->out_rows, 8 * kK));
-        const size_t smem = (size_t)gauss_steps(lw_y) * sizeof(double);
-        if (axis0_smem_opt_in(smem, lw_y)) return -1;
-        if (nan_safe)
-            TOPO_LAUNCH("gauss_axis0<nansafe>", s, gauss_axis0_kernel<true><<<grid, dim3(32, 8), smem, s>>>(p));
-        else
-            TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<false><<<grid, dim3(32, 8), smem, s>>>(p));
         cur = dst, cur_ld = dst_ld, cur_gy0 = v->out_gy0, cur_rows = v->out_rows;
     } else {
         TOPO_CHECK(v->in_gy0 <= v->out_gy0 && v->in_gy0 + v->in_rows >= v->out_gy0 + v->out_rows,
                    "input band does not cover the output rows");
     }
-    if (do_x && lw_x > kAxis1SmemMaxRadius) {
-        // wide radius: transpose -> column kernel -> transpose back (two extra 8 B/px passes are noise next
-        // to 2*lw+1 float64 FMAs per pixel)
-        const int64_t pitch = ((int64_t)v->nx + 3) & ~(int64_t)3;
-        const int64_t tpitch = ((int64_t)v->out_rows + 3) & ~(int64_t)3;
-        const size_t need = (size_t)pitch * v->out_rows * sizeof(float) + 2 * (size_t)tpitch * v->nx * sizeof(float);
-        TOPO_CHECK(ws && ws_bytes >= need, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
-        float* t1 = (float*)ws + (size_t)pitch * v->out_rows;
-        float* t2 = t1 + (size_t)tpitch * v->nx;
-        const float* src = cur + (int64_t)(v->out_gy0 - cur_gy0) * cur_ld;
+    const float* src = cur + (int64_t)(v->out_gy0 - cur_gy0) * cur_ld;  // first output row in `cur`
+    if (fx) {
+        if (fft_conv_rows(src, cur_ld, out, ld_out, v->out_rows, v->nx, 0, v->nx, 0, v->nx, w_x, lw_x, wsb + L.tables, s)) return -1;
+    } else if (do_x && lw_x > kAxis1SmemMaxRadius) {
+        // wide radius, NaN-exact: transpose -> column kernel -> transpose back
+        float* t1 = reinterpret_cast<float*>(wsb + L.t1);
+        float* t2 = reinterpret_cast<float*>(wsb + L.t2);
         dim3 tg(ceil_div(v->nx, 32), ceil_div(v->out_rows, 32));
-        TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(src, cur_ld, t1, tpitch, v->out_rows, v->nx));
-        GaussParams p{t1, t2, tpitch, tpitch, v->out_rows, v->nx, 0, v->nx, 0, v->nx, w_x, lw_x};
+        TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(src, cur_ld, t1, tp_out, v->out_rows, v->nx));
+        GaussParams p{t1, t2, tp_out, tp_out, v->out_rows, v->nx, 0, v->nx, 0, v->nx, w_x, lw_x};
         dim3 grid(ceil_div(v->out_rows, kA0Cols), ceil_div(v->nx, 8 * kK));
         const size_t smem = (size_t)gauss_steps(lw_x) * sizeof(double);
         if (axis0_smem_opt_in(smem, lw_x)) return -1;
@@ -515,7 +569,7 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
         else
             TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<false><<<grid, dim3(32, 8), smem, s>>>(p));
         dim3 tg2(ceil_div(v->out_rows, 32), ceil_div(v->nx, 32));
-        TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg2, dim3(32, 8), 0, s>>>(t2, tpitch, out, ld_out, v->nx, v->out_rows));
+        TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg2, dim3(32, 8), 0, s>>>(t2, tp_out, out, ld_out, v->nx, v->out_rows));
     } else if (do_x) {
         GaussParams p{cur, out, cur_ld, ld_out, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_x, lw_x};
         const int rc = lw_x <= 12 ? launch_axis1<8>(p, nan_safe, s) : launch_axis1<16>(p, nan_safe, s);

@@ -230,26 +230,29 @@ def _nan_result(v, like, n=1):
     return outs
 
 
-def _tsum_plan(dem, v, size, st, share, cache_size=0):
-    """T-plane sum sharing between tpi(size) and std(size) of the same integer-valued DEM band:
+def _tsum_plan(dem, v, size, st, share, cache_size=0, pair=False):
+    """Plane-sum sharing between tpi(size) and std(size) of the same DEM band (T plane of integer-valued DEMs; T and
+    fraction planes of float DEMs, only when the caller announced the pair -- a lone float tpi is cheaper unpaired):
     returns (tensor or None, op, keep) with op 0 = off, 1 = compute + keep, 2 = reuse; ``keep`` is what the caller
     publishes as ``dem._tsum`` AFTER the launch succeeded (a failed call must not leave an unwritten buffer behind)."""
     torch = _torch()
-    if not share or st["nonint"] != 0:
+    integer = st["nonint"] == 0
+    if not share or not (integer or pair):
         return None, 0, None
     L = _lib.load()
-    if not L.topo_disc_shares_tsum(ctypes.byref(v), int(size), 1, st["min"], st["max"], int(cache_size)):
+    planes = L.topo_disc_shares_tsum(ctypes.byref(v), int(size), 1 if integer else 0, st["min"], st["max"], int(cache_size))
+    if not planes:
         return None, 0, None
     key = (int(size), v.out_gy0, v.out_rows)
     cached = getattr(dem, "_tsum", None)
     dem._tsum = None  # consumed (a tpi+std pair is the use case), or replaced once the new sums exist
     if cached is not None and cached[0] == key:
         return cached[1], 2, None
-    t = torch.empty((v.out_rows, dem.nx), dtype=torch.int64, device=dem.tensor.device)
+    t = torch.empty((planes, v.out_rows, dem.nx), dtype=torch.int64, device=dem.tensor.device)
     return t, 1, (key, t)
 
 
-def _disc(name, what, dem, size, out_gy0, out_rows, out, share):
+def _disc(name, what, dem, size, out_gy0, out_rows, out, share, pair=False):
     torch = require_cuda()
     v = dem.view(out_gy0, out_rows)
     st = dem.stats
@@ -262,9 +265,12 @@ def _disc(name, what, dem, size, out_gy0, out_rows, out, share):
     cache = _plane_cache(dem, v, size, st)
     cache_size = cache.max_size if cache is not None else 0
     integer = 1 if st["nonint"] == 0 else 0
-    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), what, integer, st["min"], st["max"], cache_size)
+    # std of a float DEM reuses what a paired tpi left behind; it never starts a pair itself
+    tsum, op, keep = _tsum_plan(dem, v, size, st, share, cache_size, pair or (what == 1 and getattr(dem, "_tsum", None) is not None))
+    if what == 1 and not integer and op == 1:
+        tsum, op, keep = None, 0, None
+    ws_bytes = L.topo_disc_workspace_bytes(ctypes.byref(v), int(size), what, integer, st["min"], st["max"], cache_size, op)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dem.tensor.device)
-    tsum, op, keep = _tsum_plan(dem, v, size, st, share, cache_size)
     _lib.call(name, _ptr(dem.tensor), dem.ld, _ptr(out), int(out.stride(0)), ctypes.byref(v), int(size),
               integer, st["min"], st["max"], _ptr(tsum), op,
               ctypes.byref(cache) if cache is not None else None, _ptr(ws), ws_bytes, _stream())
@@ -309,11 +315,13 @@ def _plane_cache(dem, v, size, st):
     return cache
 
 
-def tpi(dem, size, out_gy0=None, out_rows=None, out=None, share=True):
+def tpi(dem, size, out_gy0=None, out_rows=None, out=None, share=True, pair_std=False):
     """Device TPI of global rows [out_gy0, out_gy0+out_rows); all-NaN if the DEM has non-finite values
     (the reference's FFT convolution spreads them over the whole output).  ``share``: on integer-valued
-    DEMs keep / reuse the disc sums that tpi(size) and std(size) have in common (one gather pass less per pair)."""
-    return _disc("topo_tpi_f32", 0, dem, size, out_gy0, out_rows, out, share)
+    DEMs keep / reuse the disc sums that tpi(size) and std(size) have in common (one gather pass less per pair).
+    ``pair_std``: a std(size) call follows on this DEM -- float DEMs then run the exact two-plane TPI whose plane
+    sums the std reuses (3 gather passes per pair instead of 4)."""
+    return _disc("topo_tpi_f32", 0, dem, size, out_gy0, out_rows, out, share, pair_std)
 
 
 def std(dem, size, out_gy0=None, out_rows=None, out=None, share=True):
