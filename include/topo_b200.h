@@ -182,6 +182,18 @@ int topo_grad_from_smooth_f32(const float* gx, const float* gy, int64_t ld_in, f
                               float* slope, float* aspect, int64_t ld_out, const topo_view* v,
                               const double* res_x, int res_x_2d, const double* res_y, int res_y_2d,
                               const float* res_xf, const float* res_yf, void* stream);
+/* The whole isotropic gradient (sig_ratio == 1, topo.py:630-631 + 637-642) from the raw DEM: Gaussian axis 0 ->
+ * float32 -> axis 1 -> float32 -> numpy.gradient -> resolution -> slope / aspect.  Radii up to 44 px run as ONE
+ * kernel that keeps the tile, the axis-0 result and the smoothed tile in shared memory (20 B/px of HBM traffic
+ * instead of 36; same taps in the same order: bit-identical to the separate kernels); wider radii, NaN-exact
+ * smoothing (nan_safe) and "grad_fused" switched off run topo_gauss_f32 + topo_grad_from_smooth_f32 inside `ws`
+ * (>= topo_gradient_workspace_bytes, 256-byte aligned).  w: DEVICE half kernel of lw + 1 float64 taps.  The band
+ * must cover rows out_gy0 - lw - 1 .. out_gy0 + out_rows + lw (reflected at the global edges). */
+size_t topo_gradient_workspace_bytes(const topo_view* v, int lw);
+int topo_gradient_f32(const float* dem, int64_t ld_in, float* dx, float* dy, float* slope, float* aspect,
+                      int64_t ld_out, const topo_view* v, const double* w, int lw, int nan_safe,
+                      const double* res_x, int res_x_2d, const double* res_y, int res_y_2d, const float* res_xf,
+                      const float* res_yf, void* ws, size_t ws_bytes, void* stream);
 /* Sobel branch, sigma <= 1 (topo.py:628-629, 658-685): ndimage.convolve with K/8 and K.T/8,
  * reflect borders, float64 accumulation; same normalisation / slope / aspect epilogue fused.
  * res_xf / res_yf (both entry points, optional): float32 copies of the resolution arrays, to be passed

@@ -194,3 +194,38 @@ def test_gaussian_fft_on_a_row_band_is_bit_identical():
         band = DeviceDEM(whole.tensor[a:b].contiguous(), gny=1500, gy0=a, stats=whole.stats)
         out = dev.gauss(band, sigma, sigma, lo, hi - lo)
         assert bool((out == ref[lo:hi]).all()), (lo, hi)
+
+
+@pytest.mark.parametrize("sigma", [1.25, 2.25, 5.25, 10.25])
+def test_fused_gradient_is_bit_identical_to_the_three_kernel_route(sigma):
+    """Radii up to 44 px: one kernel keeps tile + halo, the axis-0 result and the smoothed tile in shared memory and
+    finishes with np.gradient / slope / aspect.  Same taps in the same order => the same bits as gauss_axis0 ->
+    gauss_axis1 -> grad_from_smooth, on a ragged image (reflect on all four edges), with 1-D and 2-D resolutions, on
+    the whole image and on a row band; and within tolerance of the reference's own call sequence."""
+    from topo_descriptors_b200 import _lib
+
+    z = fractal_dem(333, 517, seed=20)
+    res1 = {"x": np.full(517, 25.0), "y": np.full(333, -25.0)}
+    rng = np.random.default_rng(1)
+    res2 = {"x": 25.0 + rng.uniform(-1, 1, (333, 517)), "y": -25.0 + rng.uniform(-1, 1, (333, 517))}
+    for res in (res1, res2):
+        fused = topo.gradient(z, sigma, res)
+        _lib.set_option("grad_fused", False)
+        try:
+            three = topo.gradient(z, sigma, res)
+        finally:
+            _lib.set_option("grad_fused", True)
+        for a, b, name in zip(fused, three, ("dx", "dy", "slope", "aspect")):
+            assert np.array_equal(a, b), (sigma, name, float(np.abs(a - b).max()))
+    _gradient_close(topo.gradient(z, sigma, res1), O.gradient_literal(z, sigma, res1))
+    # row band with halo lw + 1
+    lw = dev.gauss_radius(sigma)
+    whole = DeviceDEM(dev.to_device(z))
+    rx, ry = dev._Res(res1["x"], whole.tensor.device), dev._Res(res1["y"], whole.tensor.device)
+    ref = dev.gradient(whole, sigma, rx, 0, ry, 0)
+    lo, hi = 100, 250
+    a, b = max(0, lo - lw - 1), min(333, hi + lw + 1)
+    band = DeviceDEM(whole.tensor[a:b].contiguous(), gny=333, gy0=a, stats=whole.stats)
+    outs = dev.gradient(band, sigma, rx, 0, ry, 0, lo, hi - lo)
+    for o, r in zip(outs, ref):
+        assert bool((o == r[lo:hi]).all())

@@ -66,6 +66,9 @@ PROTOTYPES = {
                                c_void_p, c_size_t, c_void_p]),
     "topo_grad_from_smooth_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int64, _VP, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "topo_gradient_workspace_bytes": (c_size_t, [_VP, c_int]),
+    "topo_gradient_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, _VP, c_void_p, c_int,
+                                  c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "topo_sobel_gradient_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, _VP,
                                         c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "topo_sx_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, _VP, c_void_p, c_void_p, c_void_p,

@@ -154,9 +154,7 @@ def sweep(core, ctx, sizes, sigmas, res_x, res_y, what=("tpi", "std", "gradient"
             if sigma <= 1:
                 outs = dev.sobel_gradient(ddem, rx, rx2d, ry, ry2d, True, ctx.r0, ctx.rows)
             else:
-                g0, g1 = max(0, ctx.r0 - 1), min(ctx.gny, ctx.r1 + 1)
-                g = DeviceDEM(dev.gauss(ddem, sigma, sigma, g0, g1 - g0), gny=ctx.gny, gy0=g0, stats=stats)
-                outs = dev.gradient_from_smooth(g, g, rx, rx2d, ry, ry2d, ctx.r0, ctx.rows)
+                outs = dev.gradient(ddem, sigma, rx, rx2d, ry, ry2d, ctx.r0, ctx.rows)
             calls += 1
             if sink:
                 for nm, o in zip(("dx", "dy", "slope", "aspect"), outs):

@@ -320,6 +320,148 @@ __device__ __forceinline__ void gradient_pixel(const GradParams& p, int gy, int 
     finish_gradient(p, dx, dy, gy, x);
 }
 
+// ---- fused small-radius gradient: Gaussian axis 0 -> float32 -> axis 1 -> float32 -> np.gradient -> slope / aspect ----
+// One CTA produces a 30 x 128 tile of the four outputs from ONE read of the DEM tile + halo (20 B/px of HBM traffic
+// instead of the 36 B/px of the three-kernel route): the raw tile (32 + 2 lw rows), the axis-0 result and the smoothed
+// tile all stay in shared memory as float32 (scipy's rounding between the passes is the float32 store), every tap is
+// a float64 FMA in the same order as gauss_axis0 / gauss_axis1 (input index ascending), so the results are bit
+// identical to the three-kernel route.  Threads own 8 consecutive outputs along the filter axis (rotating weight
+// window in registers, one LDS + one F2F per sample feeds up to 8 DFMA).
+constexpr int kFuTH = 30, kFuTW = 128;       // output tile
+constexpr int kFuGR = kFuTH + 2;             // smoothed rows held per tile (one more on each side for the differences)
+constexpr int kFuGC = 136;                   // smoothed columns computed: 17 groups of 8 >= kFuTW + 2
+constexpr int kFusedMaxRadius = 44;
+
+__host__ __device__ __forceinline__ int fused_steps(int lw) { return ((8 + 2 * lw + 7) / 8) * 8; }
+
+struct FusedLayout {
+    int nst, raw_rows, raw_pitch, a_cols, a_pitch, g_pitch;
+    size_t off_raw, off_a, off_g, bytes;
+};
+
+__host__ __device__ __forceinline__ FusedLayout fused_layout(int lw) {
+    FusedLayout L;
+    L.nst = fused_steps(lw);
+    L.raw_rows = kFuGR - 8 + L.nst;           // rows walked by the last row group
+    L.a_cols = kFuGC - 8 + L.nst;             // axis-0 columns walked by the last column group
+    L.raw_pitch = L.a_cols;
+    L.a_pitch = L.a_cols | 1;                 // lanes = rows in the axis-1 pass: odd pitch, conflict-free
+    L.g_pitch = kFuGC | 1;
+    L.off_raw = (size_t)(L.nst + 16) * sizeof(double);  // weights: 8 zeros, 2 lw + 1 taps, zeros up to nst + 16
+    L.off_a = L.off_raw + (size_t)L.raw_rows * L.raw_pitch * sizeof(float);
+    L.off_g = L.off_a + (size_t)kFuGR * L.a_pitch * sizeof(float);
+    L.bytes = L.off_g + (size_t)kFuGR * L.g_pitch * sizeof(float);
+    return L;
+}
+
+__global__ void __launch_bounds__(256) gauss_grad_fused_kernel(const GradParams p, const double* __restrict__ w, int lw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FusedLayout L = fused_layout(lw);
+    double* wz = reinterpret_cast<double*>(smem_raw);
+    float* raw = reinterpret_cast<float*>(smem_raw + L.off_raw);
+    float* A = reinterpret_cast<float*>(smem_raw + L.off_a);
+    float* G = reinterpret_cast<float*>(smem_raw + L.off_g);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * kFuTW;
+    const int y0 = p.out_gy0 + blockIdx.y * kFuTH;  // global row of the tile's first output row
+    const int in_end = p.in_gy0 + p.in_rows;
+
+    // weights by step: wz[8 + n] = w[|n - lw|] for n = 0 .. 2 lw, zero elsewhere
+    for (int i = tid; i < L.nst + 16; i += 256) {
+        const int n = i - 8;
+        int a = n - lw;
+        a = a < 0 ? -a : a;
+        wz[i] = (n >= 0 && a <= lw) ? w[a] : 0.0;
+    }
+    // raw tile: row R <-> global row y0 - 1 - lw + R, column C <-> global column x0 - 1 - lw + C (reflect);
+    // rows / columns past the taps' reach are zero (they only meet zero weights)
+    const int used_rows = kFuGR + 2 * lw, used_cols = kFuTW + 2 + 2 * lw;
+    for (int R = warp; R < L.raw_rows; R += 8) {
+        float* dst = raw + R * L.raw_pitch;
+        if (R < used_rows) {
+            int g = reflect_index(y0 - 1 - lw + R, p.gny);
+            g = g < p.in_gy0 ? p.in_gy0 : (g >= in_end ? in_end - 1 : g);  // outside the band: feeds unused rows only
+            const float* src = p.gx + (int64_t)(g - p.in_gy0) * p.ld_in;
+            for (int C = lane; C < L.raw_pitch; C += 32)
+                dst[C] = C < used_cols ? __ldg(src + reflect_index(x0 - 1 - lw + C, p.nx)) : 0.f;
+        } else {
+            for (int C = lane; C < L.raw_pitch; C += 32) dst[C] = 0.f;
+        }
+    }
+    __syncthreads();
+
+    // ---- axis 0: A[r][C] = float32(sum_n w[n] raw[r + n][C]); item = (row group of 8, column), lanes = columns
+    for (int item = tid; item < (kFuGR / 8) * L.a_cols; item += 256) {
+        const int g = item / L.a_cols, C = item - g * L.a_cols;
+        const float* col = raw + (g * 8) * L.raw_pitch + C;
+        double acc[8], wr[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0, wr[k] = 0.0;
+        const double* wp = wz + 8;
+        for (int n0 = 0; n0 < L.nst; n0 += 8, wp += 8, col += 8 * L.raw_pitch) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                for (int k = 7; k > 0; --k) wr[k] = wr[k - 1];
+                wr[0] = wp[s];
+                const double d = (double)col[s * L.raw_pitch];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fma(wr[k], d, acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) A[(g * 8 + k) * L.a_pitch + C] = (float)acc[k];
+    }
+    __syncthreads();
+
+    // ---- axis 1: G[r][c] = float32(sum_n w[n] A[r][c + n]); item = (column group of 8, row), lanes = rows
+    for (int item = tid; item < (kFuGC / 8) * kFuGR; item += 256) {
+        const int gx = item / kFuGR, r = item - gx * kFuGR;
+        const float* row = A + r * L.a_pitch + gx * 8;
+        double acc[8], wr[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0, wr[k] = 0.0;
+        const double* wp = wz + 8;
+        for (int n0 = 0; n0 < L.nst; n0 += 8, wp += 8, row += 8) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                for (int k = 7; k > 0; --k) wr[k] = wr[k - 1];
+                wr[0] = wp[s];
+                const double d = (double)row[s];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fma(wr[k], d, acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) G[r * L.g_pitch + gx * 8 + k] = (float)acc[k];
+    }
+    __syncthreads();
+
+    // ---- np.gradient + resolution + slope / aspect; G[ty + 1][tx + 1] is the smoothed value of output (ty, tx)
+    const int y_end = p.out_gy0 + p.out_rows;
+    for (int i = tid; i < kFuTH * kFuTW; i += 256) {
+        const int ty = i / kFuTW, tx = i - ty * kFuTW;
+        const int gy = y0 + ty, x = x0 + tx;
+        if (gy >= y_end || x >= p.nx) continue;
+        const float* c = G + (ty + 1) * L.g_pitch + tx + 1;
+        float dx, dy;
+        if (x == 0)
+            dx = __fsub_rn(c[1], c[0]);
+        else if (x == p.nx - 1)
+            dx = __fsub_rn(c[0], c[-1]);
+        else
+            dx = __fmul_rn(__fsub_rn(c[1], c[-1]), 0.5f);
+        if (gy == 0)
+            dy = __fsub_rn(c[L.g_pitch], c[0]);
+        else if (gy == p.gny - 1)
+            dy = __fsub_rn(c[0], c[-L.g_pitch]);
+        else
+            dy = __fmul_rn(__fsub_rn(c[L.g_pitch], c[-L.g_pitch]), 0.5f);
+        finish_gradient(p, dx, dy, gy, x);
+    }
+}
+
 // block 256 = 64 pixel quads x 4 rows: tile 256 x 4.  Interior tiles of aligned rasters take the vector path
 // (128-bit loads and streaming stores, 4 pixels per thread); everything else goes pixel by pixel.
 template <bool SOBEL>
@@ -607,6 +749,78 @@ static int run_grad(bool sobel, const float* gx, const float* gy, int64_t ld_in,
     else
         TOPO_LAUNCH("grad_from_smooth", s, gradient_kernel<false><<<grid, 256, 0, s>>>(p, vec_ok));
     return 0;
+}
+
+// Rows of smoothed DEM the gradient of rows [out_gy0, out_gy0 + out_rows) reads (one more on each side, clamped)
+static void grad_smooth_rows(const topo_view* v, int& g0, int& g1) {
+    g0 = v->out_gy0 - 1 < 0 ? 0 : v->out_gy0 - 1;
+    g1 = v->out_gy0 + v->out_rows + 1 > v->gny ? v->gny : v->out_gy0 + v->out_rows + 1;
+}
+
+static bool gradient_is_fused(int lw, int nan_safe) {
+    return !nan_safe && lw >= 1 && lw <= kFusedMaxRadius && option_enabled(kOptGradFused);
+}
+
+size_t topo_gradient_workspace_bytes(const topo_view* v, int lw) {
+    if (!v) return 0;
+    // the three-kernel route (wide radii, NaN-exact smoothing, or the fused shape switched off): smoothed rows + the
+    // Gaussian's own workspace.  The fused shape needs none; the query does not know nan_safe: room for either.
+    int g0, g1;
+    grad_smooth_rows(v, g0, g1);
+    topo_view sv = *v;
+    sv.out_gy0 = g0, sv.out_rows = g1 - g0;
+    const size_t pitch = ((size_t)v->nx + 3) & ~(size_t)3;
+    const size_t smooth = (pitch * (size_t)(g1 - g0) * sizeof(float) + 255) & ~(size_t)255;
+    return smooth + topo_gauss_workspace_bytes(&sv, lw, lw);
+}
+
+int topo_gradient_f32(const float* dem, int64_t ld_in, float* dx, float* dy, float* slope, float* aspect, int64_t ld_out,
+                      const topo_view* v, const double* w, int lw, int nan_safe, const double* res_x, int res_x_2d,
+                      const double* res_y, int res_y_2d, const float* res_xf, const float* res_yf, void* ws,
+                      size_t ws_bytes, void* stream) {
+    TOPO_CHECK(dem && dx && dy && w && res_x && res_y, "null pointer");
+    if (validate_view(v)) return -1;
+    TOPO_CHECK(v->nx >= 2 && v->gny >= 2, "gradient needs at least 2 x 2 pixels");
+    TOPO_CHECK(lw >= 0, "negative radius");
+    TOPO_CHECK((slope == nullptr) == (aspect == nullptr), "slope and aspect go together");
+    TOPO_CHECK(ld_in >= v->nx && ld_out >= v->nx, "row pitch smaller than nx");
+    if (v->out_rows == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int g0, g1;
+    grad_smooth_rows(v, g0, g1);
+    if (gradient_is_fused(lw, nan_safe)) {
+        if (check_rows_reflect(v, -lw - 1, lw + 1, "fused gradient")) return -1;
+        GradParams p{dem, dem, dx, dy, slope, aspect, ld_in, ld_out, v->nx, v->gny, v->in_gy0, v->in_rows,
+                     v->out_gy0, v->out_rows, res_x, res_y, res_xf, res_yf, res_x_2d, res_y_2d, 1};
+        const FusedLayout L = fused_layout(lw);
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        TOPO_CUDA(cudaGetDevice(&dev));
+        if (dev >= 64 || !attr_set[dev]) {
+            TOPO_CUDA(cudaFuncSetAttribute(gauss_grad_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            if (dev < 64) attr_set[dev] = true;
+        }
+        dim3 grid(ceil_div(v->nx, kFuTW), ceil_div(v->out_rows, kFuTH));
+        TOPO_CHECK(grid.y <= 65535, "too many rows for one launch");
+        TOPO_LAUNCH("gauss_grad_fused", s, gauss_grad_fused_kernel<<<grid, 256, L.bytes, s>>>(p, w, lw));
+        return 0;
+    }
+    // three kernels: smooth rows [g0, g1), then differentiate
+    topo_view sv = *v;
+    sv.out_gy0 = g0, sv.out_rows = g1 - g0;
+    const int64_t pitch = ((int64_t)v->nx + 3) & ~(int64_t)3;
+    const size_t smooth = ((size_t)pitch * (size_t)(g1 - g0) * sizeof(float) + 255) & ~(size_t)255;
+    TOPO_CHECK(ws && ws_bytes >= smooth + topo_gauss_workspace_bytes(&sv, lw, lw), "workspace too small: need %zu bytes, got %zu",
+               smooth + topo_gauss_workspace_bytes(&sv, lw, lw), ws_bytes);
+    TOPO_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+    float* sm = reinterpret_cast<float*>(ws);
+    int rc = topo_gauss_f32(dem, ld_in, sm, pitch, &sv, w, lw, w, lw, nan_safe, reinterpret_cast<unsigned char*>(ws) + smooth,
+                            ws_bytes - smooth, stream);
+    if (rc) return rc;
+    topo_view gv = *v;
+    gv.in_gy0 = g0, gv.in_rows = g1 - g0;
+    return run_grad(false, sm, sm, pitch, dx, dy, slope, aspect, ld_out, &gv, res_x, res_x_2d, res_y, res_y_2d, res_xf, res_yf, 1,
+                    stream);
 }
 
 int topo_grad_from_smooth_f32(const float* gx, const float* gy, int64_t ld_in, float* dx, float* dy, float* slope,

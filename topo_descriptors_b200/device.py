@@ -371,6 +371,27 @@ def gradient_from_smooth(gx, gy, res_x_dev, res_x_2d, res_y_dev, res_y_2d, out_g
     return outs
 
 
+def gradient(dem, sigma, res_x_dev, res_x_2d, res_y_dev, res_y_2d, out_gy0=None, out_rows=None):
+    """[dx, dy, slope, aspect] of the Gaussian-smoothed DEM (isotropic sigma > 1) for global rows
+    [out_gy0, out_gy0+out_rows): one fused kernel for radii up to 44 px, else smoothing + differences inside the
+    library's workspace.  The band must reach ``gauss_radius(sigma) + 1`` rows beyond the output rows."""
+    torch = require_cuda()
+    v = dem.view(out_gy0, out_rows)
+    w, lw = _device_weights(sigma, dem.tensor.device)
+    rx, ry = _as_res(res_x_dev, res_x_2d), _as_res(res_y_dev, res_y_2d)
+    f32 = rx.f32 is not None and ry.f32 is not None
+    st = dem._stats if dem._stats is not None else (dem.stats if dem.is_whole else None)
+    nan_safe = 1 if (st is None or st["nonfinite"] > 0) else 0
+    outs = [_new(v.out_rows, dem.nx, dem.tensor) for _ in range(4)]
+    ws_bytes = _lib.load().topo_gradient_workspace_bytes(ctypes.byref(v), lw)
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dem.tensor.device)
+    base = (ws.data_ptr() + 255) & ~255
+    _lib.call("topo_gradient_f32", _ptr(dem.tensor), dem.ld, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(outs[3]),
+              int(outs[0].stride(0)), ctypes.byref(v), _ptr(w), lw, nan_safe, _ptr(rx.f64), rx.is_2d, _ptr(ry.f64), ry.is_2d,
+              _ptr(rx.f32 if f32 else None), _ptr(ry.f32 if f32 else None), ctypes.c_void_p(base), ws_bytes, _stream())
+    return outs
+
+
 def sobel_gradient(dem, res_x_dev=None, res_x_2d=0, res_y_dev=None, res_y_2d=0, normalize=True, out_gy0=None,
                    out_rows=None):
     """Sobel derivatives; with ``normalize`` also the resolution division + slope + aspect."""

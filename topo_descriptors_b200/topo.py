@@ -344,12 +344,12 @@ def gradient(dem, sigma, res_meters, sig_ratio=1):
         if not d.is_whole:
             raise ValueError("gradient of a row band goes through bands.py (needs a halo)")
         if sig_ratio == 1:
-            gx = gy = DeviceDEM(dev.gauss(d, sigma, sigma))
+            outs = dev.gradient(d, sigma, rx, rx2d, ry, ry2d)
         else:
             sigma_perp = sigma * sig_ratio
             gx = DeviceDEM(dev.gauss(d, sigma_perp, sigma))
             gy = DeviceDEM(dev.gauss(d, sigma, sigma_perp))
-        outs = dev.gradient_from_smooth(gx, gy, rx, rx2d, ry, ry2d)
+            outs = dev.gradient_from_smooth(gx, gy, rx, rx2d, ry, ry2d)
     return [m.back(o, np.float32) for o in outs]
 
 
