@@ -183,7 +183,7 @@ int topo_grad_from_smooth_f32(const float* gx, const float* gy, int64_t ld_in, f
                               const double* res_x, int res_x_2d, const double* res_y, int res_y_2d,
                               const float* res_xf, const float* res_yf, void* stream);
 /* The whole isotropic gradient (sig_ratio == 1, topo.py:630-631 + 637-642) from the raw DEM: Gaussian axis 0 ->
- * float32 -> axis 1 -> float32 -> numpy.gradient -> resolution -> slope / aspect.  Radii up to 44 px run as ONE
+ * float32 -> axis 1 -> float32 -> numpy.gradient -> resolution -> slope / aspect.  Radii up to 21 px run as ONE
  * kernel that keeps the tile, the axis-0 result and the smoothed tile in shared memory (20 B/px of HBM traffic
  * instead of 36; same taps in the same order: bit-identical to the separate kernels); wider radii, NaN-exact
  * smoothing (nan_safe) and "grad_fused" switched off run topo_gauss_f32 + topo_grad_from_smooth_f32 inside `ws`

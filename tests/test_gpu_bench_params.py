@@ -198,7 +198,7 @@ def test_gaussian_fft_on_a_row_band_is_bit_identical():
 
 @pytest.mark.parametrize("sigma", [1.25, 2.25, 5.25, 10.25])
 def test_fused_gradient_is_bit_identical_to_the_three_kernel_route(sigma):
-    """Radii up to 44 px: one kernel keeps tile + halo, the axis-0 result and the smoothed tile in shared memory and
+    """Radii up to 21 px: one kernel keeps tile + halo, the axis-0 result and the smoothed tile in shared memory and
     finishes with np.gradient / slope / aspect.  Same taps in the same order => the same bits as gauss_axis0 ->
     gauss_axis1 -> grad_from_smooth, on a ragged image (reflect on all four edges), with 1-D and 2-D resolutions, on
     the whole image and on a row band; and within tolerance of the reference's own call sequence."""

@@ -11,8 +11,12 @@
 // applied while staging) and lanes = rows with an odd pitch (conflict-free), outputs are transposed
 // back through shared memory for coalesced stores.
 #include <math.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace topo {
 
@@ -321,144 +325,235 @@ __device__ __forceinline__ void gradient_pixel(const GradParams& p, int gy, int 
 }
 
 // ---- fused small-radius gradient: Gaussian axis 0 -> float32 -> axis 1 -> float32 -> np.gradient -> slope / aspect ----
-// One CTA produces a 30 x 128 tile of the four outputs from ONE read of the DEM tile + halo (20 B/px of HBM traffic
-// instead of the 36 B/px of the three-kernel route): the raw tile (32 + 2 lw rows), the axis-0 result and the smoothed
-// tile all stay in shared memory as float32 (scipy's rounding between the passes is the float32 store), every tap is
-// a float64 FMA in the same order as gauss_axis0 / gauss_axis1 (input index ascending), so the results are bit
-// identical to the three-kernel route.  Threads own 8 consecutive outputs along the filter axis (rotating weight
-// window in registers, one LDS + one F2F per sample feeds up to 8 DFMA).
+// A persistent CTA walks 30 x 128 output tiles and produces the four outputs from ONE read of the DEM tile + halo
+// (20 B/px of HBM traffic instead of the 36 B/px of the three-kernel route).  The raw tile arrives by TMA
+// (cp.async.bulk.tensor.2d + mbarrier; with two buffers the next tile is in flight while this one is computed; tiles
+// that touch an image edge are staged by hand with the reflect rule).  The raw tile (float32), the axis-0 result
+// (rounded to float32 like scipy's intermediate array, kept as float64 so the second pass needs no conversion) and the
+// smoothed tile stay in shared memory.  Every tap is a float64 FMA in the same order as gauss_axis0 / gauss_axis1
+// (input index ascending), so the results are bit identical to the three-kernel route.  A thread owns 8 consecutive
+// outputs along the filter axis; the half kernel sits in (uniform) registers (template radius LWT >= lw, weights
+// beyond lw are zero: fma(0, x, acc) = acc) and all tap indices are compile-time, so exactly 8 (2 LWT + 1) DFMA are
+// issued per 8 + 2 LWT samples.
 constexpr int kFuTH = 30, kFuTW = 128;       // output tile
 constexpr int kFuGR = kFuTH + 2;             // smoothed rows held per tile (one more on each side for the differences)
-constexpr int kFuGC = 136;                   // smoothed columns computed: 17 groups of 8 >= kFuTW + 2
-constexpr int kFusedMaxRadius = 44;
+constexpr int kFuGC = 136;                   // smoothed columns computed (17 groups of 8): column c <-> x0 - 4 + c
+constexpr int kFuGP = 140;                   // pitch of the smoothed tile (multiple of 4: aligned 128-bit reads)
+constexpr int kFusedMaxRadius = 21;
 
-__host__ __device__ __forceinline__ int fused_steps(int lw) { return ((8 + 2 * lw + 7) / 8) * 8; }
-
-struct FusedLayout {
-    int nst, raw_rows, raw_pitch, a_cols, a_pitch, g_pitch;
-    size_t off_raw, off_a, off_g, bytes;
+template <int LWT>
+struct FusedShape {
+    static constexpr int NBUF = LWT <= 5 ? 2 : 1;              // raw-tile buffers (2: the next tile's copy overlaps the whole tile;
+                                                                // 1: it is issued after the axis-0 pass) -- sized for 2 CTAs per SM
+    using AT = typename std::conditional<(LWT <= 13), double, float>::type;  // axis-0 result: float64 saves the second pass its
+                                                                             // conversions, float32 halves the buffer
+    static constexpr int HL = (4 + LWT + 3) & ~3;               // raw column C <-> global column x0 - HL + C (16-byte aligned box)
+    static constexpr int OFF = HL - 4 - LWT;                    // smoothed column c, tap n reads raw / axis-0 column c + n + OFF
+    static constexpr int RAW_ROWS = kFuGR + 2 * LWT;            // raw row R <-> global row y0 - 1 - LWT + R
+    static constexpr int NEED_COLS = kFuTW + 2 + 2 * LWT + OFF + 3;  // last raw column a needed output reads, + 1
+    static constexpr int RAW_COLS = (kFuGC + 2 * LWT + OFF + 3) & ~3;
+    static constexpr int A_PITCH = RAW_COLS | 1;                // elements; lanes = rows in the axis-1 pass: odd pitch
+    static constexpr size_t RAW_BYTES = (size_t)RAW_ROWS * RAW_COLS * sizeof(float);
+    static constexpr size_t RAW_STRIDE = (RAW_BYTES + 127) & ~(size_t)127;  // TMA destinations are 128-byte aligned
+    static constexpr size_t OFF_A = NBUF * RAW_STRIDE;
+    static constexpr size_t OFF_G = (OFF_A + (size_t)kFuGR * A_PITCH * sizeof(AT) + 15) & ~(size_t)15;
+    static constexpr size_t OFF_BAR = (OFF_G + (size_t)kFuGR * kFuGP * sizeof(float) + 15) & ~(size_t)15;
+    static constexpr size_t BYTES = OFF_BAR + 2 * sizeof(uint64_t);
 };
 
-__host__ __device__ __forceinline__ FusedLayout fused_layout(int lw) {
-    FusedLayout L;
-    L.nst = fused_steps(lw);
-    L.raw_rows = kFuGR - 8 + L.nst;           // rows walked by the last row group
-    L.a_cols = kFuGC - 8 + L.nst;             // axis-0 columns walked by the last column group
-    L.raw_pitch = L.a_cols;
-    L.a_pitch = L.a_cols | 1;                 // lanes = rows in the axis-1 pass: odd pitch, conflict-free
-    L.g_pitch = kFuGC | 1;
-    L.off_raw = (size_t)(L.nst + 16) * sizeof(double);  // weights: 8 zeros, 2 lw + 1 taps, zeros up to nst + 16
-    L.off_a = L.off_raw + (size_t)L.raw_rows * L.raw_pitch * sizeof(float);
-    L.off_g = L.off_a + (size_t)kFuGR * L.a_pitch * sizeof(float);
-    L.bytes = L.off_g + (size_t)kFuGR * L.g_pitch * sizeof(float);
-    return L;
+// acc[k] += w[|s - k - LWT|] * x for the outputs k = 0..7 that sample s (0 .. 7 + 2 LWT) reaches
+template <int LWT, int S>
+__device__ __forceinline__ void fused_taps(double (&acc)[8], const double (&w)[LWT + 1], double x) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int n = S - k;
+        if (n >= 0 && n <= 2 * LWT) acc[k] = fma(w[n < LWT ? LWT - n : n - LWT], x, acc[k]);
+    }
 }
 
-__global__ void __launch_bounds__(256) gauss_grad_fused_kernel(const GradParams p, const double* __restrict__ w, int lw) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const FusedLayout L = fused_layout(lw);
-    double* wz = reinterpret_cast<double*>(smem_raw);
-    float* raw = reinterpret_cast<float*>(smem_raw + L.off_raw);
-    float* A = reinterpret_cast<float*>(smem_raw + L.off_a);
-    float* G = reinterpret_cast<float*>(smem_raw + L.off_g);
+template <int LWT, int S = 0>
+struct FusedWalk {
+    template <class Load>
+    __device__ __forceinline__ static void run(double (&acc)[8], const double (&w)[LWT + 1], Load load) {
+        fused_taps<LWT, S>(acc, w, load(S));
+        if constexpr (S + 1 < 8 + 2 * LWT) FusedWalk<LWT, S + 1>::run(acc, w, load);
+    }
+};
+
+struct FusedParams {
+    GradParams g;
+    const double* w;
+    int lw, vec_ok, use_tma, tiles_x, tiles_y;
+};
+
+template <int LWT>
+__global__ void __launch_bounds__(256) gauss_grad_fused_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams q) {
+    using SH = FusedShape<LWT>;
+    const GradParams& p = q.g;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using AT = typename SH::AT;
+    AT* A = reinterpret_cast<AT*>(smem_raw + SH::OFF_A);
+    float* G = reinterpret_cast<float*>(smem_raw + SH::OFF_G);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + SH::OFF_BAR);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * kFuTW;
-    const int y0 = p.out_gy0 + blockIdx.y * kFuTH;  // global row of the tile's first output row
     const int in_end = p.in_gy0 + p.in_rows;
-
-    // weights by step: wz[8 + n] = w[|n - lw|] for n = 0 .. 2 lw, zero elsewhere
-    for (int i = tid; i < L.nst + 16; i += 256) {
-        const int n = i - 8;
-        int a = n - lw;
-        a = a < 0 ? -a : a;
-        wz[i] = (n >= 0 && a <= lw) ? w[a] : 0.0;
-    }
-    // raw tile: row R <-> global row y0 - 1 - lw + R, column C <-> global column x0 - 1 - lw + C (reflect);
-    // rows / columns past the taps' reach are zero (they only meet zero weights)
-    const int used_rows = kFuGR + 2 * lw, used_cols = kFuTW + 2 + 2 * lw;
-    for (int R = warp; R < L.raw_rows; R += 8) {
-        float* dst = raw + R * L.raw_pitch;
-        if (R < used_rows) {
-            int g = reflect_index(y0 - 1 - lw + R, p.gny);
-            g = g < p.in_gy0 ? p.in_gy0 : (g >= in_end ? in_end - 1 : g);  // outside the band: feeds unused rows only
-            const float* src = p.gx + (int64_t)(g - p.in_gy0) * p.ld_in;
-            for (int C = lane; C < L.raw_pitch; C += 32)
-                dst[C] = C < used_cols ? __ldg(src + reflect_index(x0 - 1 - lw + C, p.nx)) : 0.f;
-        } else {
-            for (int C = lane; C < L.raw_pitch; C += 32) dst[C] = 0.f;
-        }
-    }
-    __syncthreads();
-
-    // ---- axis 0: A[r][C] = float32(sum_n w[n] raw[r + n][C]); item = (row group of 8, column), lanes = columns
-    for (int item = tid; item < (kFuGR / 8) * L.a_cols; item += 256) {
-        const int g = item / L.a_cols, C = item - g * L.a_cols;
-        const float* col = raw + (g * 8) * L.raw_pitch + C;
-        double acc[8], wr[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.0, wr[k] = 0.0;
-        const double* wp = wz + 8;
-        for (int n0 = 0; n0 < L.nst; n0 += 8, wp += 8, col += 8 * L.raw_pitch) {
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-#pragma unroll
-                for (int k = 7; k > 0; --k) wr[k] = wr[k - 1];
-                wr[0] = wp[s];
-                const double d = (double)col[s * L.raw_pitch];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fma(wr[k], d, acc[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) A[(g * 8 + k) * L.a_pitch + C] = (float)acc[k];
-    }
-    __syncthreads();
-
-    // ---- axis 1: G[r][c] = float32(sum_n w[n] A[r][c + n]); item = (column group of 8, row), lanes = rows
-    for (int item = tid; item < (kFuGC / 8) * kFuGR; item += 256) {
-        const int gx = item / kFuGR, r = item - gx * kFuGR;
-        const float* row = A + r * L.a_pitch + gx * 8;
-        double acc[8], wr[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.0, wr[k] = 0.0;
-        const double* wp = wz + 8;
-        for (int n0 = 0; n0 < L.nst; n0 += 8, wp += 8, row += 8) {
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-#pragma unroll
-                for (int k = 7; k > 0; --k) wr[k] = wr[k - 1];
-                wr[0] = wp[s];
-                const double d = (double)row[s];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fma(wr[k], d, acc[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) G[r * L.g_pitch + gx * 8 + k] = (float)acc[k];
-    }
-    __syncthreads();
-
-    // ---- np.gradient + resolution + slope / aspect; G[ty + 1][tx + 1] is the smoothed value of output (ty, tx)
     const int y_end = p.out_gy0 + p.out_rows;
-    for (int i = tid; i < kFuTH * kFuTW; i += 256) {
-        const int ty = i / kFuTW, tx = i - ty * kFuTW;
-        const int gy = y0 + ty, x = x0 + tx;
-        if (gy >= y_end || x >= p.nx) continue;
-        const float* c = G + (ty + 1) * L.g_pitch + tx + 1;
-        float dx, dy;
-        if (x == 0)
-            dx = __fsub_rn(c[1], c[0]);
-        else if (x == p.nx - 1)
-            dx = __fsub_rn(c[0], c[-1]);
-        else
-            dx = __fmul_rn(__fsub_rn(c[1], c[-1]), 0.5f);
-        if (gy == 0)
-            dy = __fsub_rn(c[L.g_pitch], c[0]);
-        else if (gy == p.gny - 1)
-            dy = __fsub_rn(c[0], c[-L.g_pitch]);
-        else
-            dy = __fmul_rn(__fsub_rn(c[L.g_pitch], c[-L.g_pitch]), 0.5f);
-        finish_gradient(p, dx, dy, gy, x);
+    const int ntiles = q.tiles_x * q.tiles_y;
+
+    double w[LWT + 1];
+#pragma unroll
+    for (int i = 0; i <= LWT; ++i) w[i] = i <= q.lw ? __ldg(q.w + i) : 0.0;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // a tile whose box lies inside the image and the band is copied by TMA; the others are staged by hand (reflect)
+    auto tile_origin = [&](int t, int& x0, int& y0) {
+        const int by = t / q.tiles_x;
+        x0 = (t - by * q.tiles_x) * kFuTW;
+        y0 = p.out_gy0 + by * kFuTH;
+    };
+    auto by_tma = [&](int t) {
+        int x0, y0;
+        tile_origin(t, x0, y0);
+        const int r0 = y0 - 1 - LWT;
+        return q.use_tma && x0 - SH::HL >= 0 && x0 - SH::HL + SH::NEED_COLS <= p.nx && r0 >= 0 && r0 >= p.in_gy0 &&
+               r0 + SH::RAW_ROWS <= p.gny && r0 + SH::RAW_ROWS <= in_end;
+    };
+    auto issue = [&](int t, int buf) {  // thread 0 only
+        int x0, y0;
+        tile_origin(t, x0, y0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bar[buf], (uint32_t)SH::RAW_BYTES);
+        tma_load_2d(smem_raw + buf * SH::RAW_STRIDE, &tmap, x0 - SH::HL, y0 - 1 - LWT - p.in_gy0, &bar[buf]);
+    };
+
+    uint32_t phases = 0u;  // bit b: parity the next completion of bar[b] will have
+    const int t0 = blockIdx.x, stride = gridDim.x;
+    if (t0 < ntiles && by_tma(t0) && tid == 0) issue(t0, 0);
+    for (int it = 0, t = t0; t < ntiles; ++it, t += stride) {
+        const int buf = SH::NBUF == 2 ? (it & 1) : 0;
+        float* raw = reinterpret_cast<float*>(smem_raw + buf * SH::RAW_STRIDE);
+        int x0, y0;
+        tile_origin(t, x0, y0);
+        if (SH::NBUF == 2) {  // next tile in flight while this one is computed (its buffer was last read two syncs ago)
+            const int nt = t + stride;
+            if (nt < ntiles && by_tma(nt) && tid == 0) issue(nt, buf ^ 1);
+        }
+        if (by_tma(t)) {
+            mbar_wait(&bar[buf], (phases >> buf) & 1u);
+            phases ^= 1u << buf;
+        } else {
+            for (int R = warp; R < SH::RAW_ROWS; R += 8) {
+                int g = reflect_index(y0 - 1 - LWT + R, p.gny);
+                g = g < p.in_gy0 ? p.in_gy0 : (g >= in_end ? in_end - 1 : g);  // outside the band: rows no stored output reads
+                const float* src = p.gx + (int64_t)(g - p.in_gy0) * p.ld_in;
+                float* dst = raw + R * SH::RAW_COLS;
+                for (int C = lane; C < SH::RAW_COLS; C += 32) dst[C] = __ldg(src + reflect_index(x0 - SH::HL + C, p.nx));
+            }
+            __syncthreads();
+        }
+
+        // ---- axis 0: A[r][C] = float32(sum_n w[n] raw[r + n][C]); item = (row group of 8, column), lanes = columns
+        for (int item = tid; item < (kFuGR / 8) * SH::RAW_COLS; item += 256) {
+            const int g = item / SH::RAW_COLS, C = item - g * SH::RAW_COLS;
+            const float* col = raw + (g * 8) * SH::RAW_COLS + C;
+            double acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+            FusedWalk<LWT>::run(acc, w, [&](int s) { return (double)col[s * SH::RAW_COLS]; });
+#pragma unroll
+            for (int k = 0; k < 8; ++k) A[(g * 8 + k) * SH::A_PITCH + C] = (AT)(float)acc[k];
+        }
+        __syncthreads();
+        if (SH::NBUF == 1) {  // single buffer: the raw tile is free now, start the next copy under the remaining phases
+            const int nt = t + stride;
+            if (nt < ntiles && by_tma(nt) && tid == 0) issue(nt, 0);
+        }
+
+        // ---- axis 1: G[r][c] = float32(sum_n w[n] A[r][c + n + OFF]); item = (column group of 8, row), lanes = rows
+        for (int item = tid; item < (kFuGC / 8) * kFuGR; item += 256) {
+            const int gx = item / kFuGR, r = item - gx * kFuGR;
+            const AT* row = A + r * SH::A_PITCH + gx * 8 + SH::OFF;
+            double acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+            FusedWalk<LWT>::run(acc, w, [&](int s) { return (double)row[s]; });
+#pragma unroll
+            for (int k = 0; k < 8; ++k) G[r * kFuGP + gx * 8 + k] = (float)acc[k];
+        }
+        __syncthreads();
+
+        // ---- np.gradient + resolution + slope / aspect; G[ty + 1][tx + 4] is the smoothed value of output (ty, tx).
+        // 4 pixels per thread; interior quads of aligned rasters with float32 resolutions take 128-bit loads / stores.
+        for (int i = tid; i < kFuTH * (kFuTW / 4); i += 256) {
+            const int ty = i / (kFuTW / 4), tx = (i - ty * (kFuTW / 4)) * 4;
+            const int gy = y0 + ty, x = x0 + tx;
+            if (gy >= y_end || x >= p.nx) continue;
+            const float* c = G + (ty + 1) * kFuGP + tx + 4;
+            const bool quad = q.vec_ok && x >= 1 && x + 4 < p.nx && gy >= 1 && gy + 1 < p.gny;
+            if (quad) {
+                const float4 mid = *reinterpret_cast<const float4*>(c);
+                const float4 up = *reinterpret_cast<const float4*>(c - kFuGP), dn = *reinterpret_cast<const float4*>(c + kFuGP);
+                const float v[6] = {c[-1], mid.x, mid.y, mid.z, mid.w, c[4]};
+                const float u[4] = {up.x, up.y, up.z, up.w}, d[4] = {dn.x, dn.y, dn.z, dn.w};
+                float dxv[4], dyv[4], rxv[4], ryv[4], sl[4], as[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dxv[j] = __fmul_rn(__fsub_rn(v[j + 2], v[j]), 0.5f);
+                    dyv[j] = __fmul_rn(__fsub_rn(d[j], u[j]), 0.5f);
+                }
+                const float4 tx4 = ldg4(p.res_xf + (p.res_x_2d ? (int64_t)gy * p.nx : 0) + x);
+                rxv[0] = tx4.x, rxv[1] = tx4.y, rxv[2] = tx4.z, rxv[3] = tx4.w;
+                if (p.res_y_2d) {
+                    const float4 t4 = ldg4(p.res_yf + (int64_t)gy * p.nx + x);
+                    ryv[0] = t4.x, ryv[1] = t4.y, ryv[2] = t4.z, ryv[3] = t4.w;
+                } else {
+                    ryv[0] = ryv[1] = ryv[2] = ryv[3] = __ldg(p.res_yf + gy);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dxv[j] = __fdiv_rn(dxv[j], rxv[j]);
+                    dyv[j] = __fdiv_rn(dyv[j], ryv[j]);
+                }
+                const int64_t o = (int64_t)(gy - p.out_gy0) * p.ld_out + x;
+                st4_streaming(p.dx + o, make_float4(dxv[0], dxv[1], dxv[2], dxv[3]));
+                st4_streaming(p.dy + o, make_float4(dyv[0], dyv[1], dyv[2], dyv[3]));
+                if (p.slope) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) slope_aspect(dxv[j], dyv[j], sl[j], as[j]);
+                    st4_streaming(p.slope + o, make_float4(sl[0], sl[1], sl[2], sl[3]));
+                    st4_streaming(p.aspect + o, make_float4(as[0], as[1], as[2], as[3]));
+                }
+                continue;
+            }
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const int xx = x + j;
+                if (xx >= p.nx) break;
+                float dx, dy;
+                if (xx == 0)
+                    dx = __fsub_rn(c[j + 1], c[j]);
+                else if (xx == p.nx - 1)
+                    dx = __fsub_rn(c[j], c[j - 1]);
+                else
+                    dx = __fmul_rn(__fsub_rn(c[j + 1], c[j - 1]), 0.5f);
+                if (gy == 0)
+                    dy = __fsub_rn(c[j + kFuGP], c[j]);
+                else if (gy == p.gny - 1)
+                    dy = __fsub_rn(c[j], c[j - kFuGP]);
+                else
+                    dy = __fmul_rn(__fsub_rn(c[j + kFuGP], c[j - kFuGP]), 0.5f);
+                finish_gradient(p, dx, dy, gy, xx);
+            }
+        }
+        // (no barrier: the next iteration writes the other raw buffer / A only after its own barriers, and G is not
+        // written before the barrier that follows the next axis-0 pass)
+        if (SH::NBUF == 1) __syncthreads();  // hand-staged tiles write the single raw buffer right away
     }
 }
 
@@ -792,17 +887,39 @@ int topo_gradient_f32(const float* dem, int64_t ld_in, float* dx, float* dy, flo
         if (check_rows_reflect(v, -lw - 1, lw + 1, "fused gradient")) return -1;
         GradParams p{dem, dem, dx, dy, slope, aspect, ld_in, ld_out, v->nx, v->gny, v->in_gy0, v->in_rows,
                      v->out_gy0, v->out_rows, res_x, res_y, res_xf, res_yf, res_x_2d, res_y_2d, 1};
-        const FusedLayout L = fused_layout(lw);
-        static bool attr_set[64] = {false};
-        int dev = 0;
-        TOPO_CUDA(cudaGetDevice(&dev));
-        if (dev >= 64 || !attr_set[dev]) {
-            TOPO_CUDA(cudaFuncSetAttribute(gauss_grad_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            if (dev < 64) attr_set[dev] = true;
-        }
-        dim3 grid(ceil_div(v->nx, kFuTW), ceil_div(v->out_rows, kFuTH));
-        TOPO_CHECK(grid.y <= 65535, "too many rows for one launch");
-        TOPO_LAUNCH("gauss_grad_fused", s, gauss_grad_fused_kernel<<<grid, 256, L.bytes, s>>>(p, w, lw));
+        auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        FusedParams fp;
+        fp.g = p, fp.w = w, fp.lw = lw;
+        fp.vec_ok = (ld_out % 4 == 0) && (v->nx % 4 == 0) && al16(dx) && al16(dy) && (!slope || (al16(slope) && al16(aspect))) &&
+                    res_xf && res_yf && al16(res_xf) && al16(res_yf);
+        fp.tiles_x = ceil_div(v->nx, kFuTW), fp.tiles_y = ceil_div(v->out_rows, kFuTH);
+        TOPO_CHECK((long long)fp.tiles_x * fp.tiles_y < 2147483647ll, "too many tiles");
+        const int ntiles = fp.tiles_x * fp.tiles_y;
+#define TOPO_FUSED_LAUNCH(LWT)                                                                                           \
+    do {                                                                                                                 \
+        using SH = FusedShape<LWT>;                                                                                      \
+        static bool attr_set[64] = {false};                                                                              \
+        int dev = 0;                                                                                                     \
+        TOPO_CUDA(cudaGetDevice(&dev));                                                                                  \
+        if (dev >= 64 || !attr_set[dev]) {                                                                               \
+            TOPO_CUDA(cudaFuncSetAttribute(gauss_grad_fused_kernel<LWT>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           (int)SH::BYTES));                                                             \
+            if (dev < 64) attr_set[dev] = true;                                                                          \
+        }                                                                                                                \
+        CUtensorMap tmap;                                                                                                \
+        memset(&tmap, 0, sizeof(tmap));                                                                                  \
+        fp.use_tma = make_tmap_2d_f32(&tmap, dem, (uint64_t)v->nx, (uint64_t)v->in_rows, (uint64_t)ld_in, SH::RAW_COLS,  \
+                                      SH::RAW_ROWS) ? 1 : 0;                                                             \
+        const int per_sm = (int)(227 * 1024 / (SH::BYTES + 1024));                                                       \
+        int ctas = kNumSMs * (per_sm < 1 ? 1 : per_sm);                                                                  \
+        if (ctas > ntiles) ctas = ntiles;                                                                                \
+        TOPO_LAUNCH("gauss_grad_fused", s, gauss_grad_fused_kernel<LWT><<<ctas, 256, SH::BYTES, s>>>(tmap, fp));         \
+    } while (0)
+        if (lw <= 5) TOPO_FUSED_LAUNCH(5);
+        else if (lw <= 9) TOPO_FUSED_LAUNCH(9);
+        else if (lw <= 13) TOPO_FUSED_LAUNCH(13);
+        else TOPO_FUSED_LAUNCH(21);
+#undef TOPO_FUSED_LAUNCH
         return 0;
     }
     // three kernels: smooth rows [g0, g1), then differentiate

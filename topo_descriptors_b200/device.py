@@ -373,7 +373,7 @@ def gradient_from_smooth(gx, gy, res_x_dev, res_x_2d, res_y_dev, res_y_2d, out_g
 
 def gradient(dem, sigma, res_x_dev, res_x_2d, res_y_dev, res_y_2d, out_gy0=None, out_rows=None):
     """[dx, dy, slope, aspect] of the Gaussian-smoothed DEM (isotropic sigma > 1) for global rows
-    [out_gy0, out_gy0+out_rows): one fused kernel for radii up to 44 px, else smoothing + differences inside the
+    [out_gy0, out_gy0+out_rows): one fused kernel for radii up to 21 px, else smoothing + differences inside the
     library's workspace.  The band must reach ``gauss_radius(sigma) + 1`` rows beyond the output rows."""
     torch = require_cuda()
     v = dem.view(out_gy0, out_rows)
