@@ -235,6 +235,27 @@ int topo_sx_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int
  * banks of <= 4 and calls once per bank with group_flags bit 0 = "norm / dir hold the raw running (max, argmax) of
  * the previous banks" and bit 1 = "leave them raw for the next bank" (0 for a single bank); ties between banks
  * resolve to the lower angle, which is the reference's strict '>' over the angles in order. */
+/* Device-side rotation of the kernel bank (topo.py:521-531 + the channel mixing of topo.py:431,443) for the FFT route:
+ * coef (DEVICE): the n_kernels source kernels (h x w each) after scipy's quadratic-spline prefilter, float64;
+ * angles (DEVICE): n_angles records of 64 bytes {double m00, m01, m10, m11, off0, off1; int64 out_off; int32 oh, ow}
+ * = rotation matrix, offset and output box of scipy.ndimage.rotate(reshape=True) for each angle (computed by the host
+ * with scipy's own cosdg / sindg) and the element offset of the angle's [n_kernels][oh][ow] block.  scratch and out
+ * (DEVICE): as many floats as the blocks take.  out receives the rotated (order-2 spline, exactly scipy's arithmetic),
+ * masked (cval), z-scored and channel-mixed kernels in scipy's orientation -- the `kernels` of
+ * topo_valley_ridge_fft_f32. */
+int topo_rotate_bank_f32(const double* coef, int n_kernels, int h, int w, const void* angles, int n_angles, float cval,
+                         float* scratch, float* out, void* stream);
+/* Large kernels: the same bank applied by 2-D overlap-save FFT convolution (float64 transforms in shared memory,
+ * two real kernels per complex transform, spectra of the image tiles computed once): the cost per (angle, channel)
+ * kernel is one inverse 2-D transform per tile, whatever the kernel size -- like the reference's own
+ * signal.convolve, which takes its FFT method (topo.py:443).  kernels (DEVICE): the channel-mixed kernels in scipy's
+ * orientation (true convolution, NOT flipped), row-major, kernel i at element offset kern_off[i]; kern_off / kern_hw
+ * (HOST): per kernel its offset and (h, w, angle index), in angle order; hmax / wmax: maxima over the bank (up to 4096).
+ * ws: DEVICE, 256-byte aligned, >= the query (3 x tiles x T^2 x 16 B, T = 2048 / 4096 / 8192). */
+size_t topo_valley_ridge_fft_workspace_bytes(const topo_view* v, int hmax, int wmax);
+int topo_valley_ridge_fft_f32(const float* dem_norm, int64_t ld_in, float* norm, float* dir, int64_t ld_out,
+                              const topo_view* v, const float* kernels, const long long* kern_off, const int* kern_hw,
+                              int n_kernels, int hmax, int wmax, void* ws, size_t ws_bytes, void* stream);
 int topo_zscore_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, int rows, int nx,
                     float mean, float std, void* stream);
 int topo_valley_ridge_f32(const float* dem_norm, int64_t ld_in, float* norm, float* dir, int64_t ld_out,

@@ -229,3 +229,95 @@ def test_fused_gradient_is_bit_identical_to_the_three_kernel_route(sigma):
     outs = dev.gradient(band, sigma, rx, 0, ry, 0, lo, hi - lo)
     for o, r in zip(outs, ref):
         assert bool((o == r[lo:hi]).all())
+
+
+def test_out_of_core_tiler_is_bit_identical_to_the_resident_path(tmp_path):
+    """a DEM streamed through HBM in row bands (the reference's dask map_overlap case, topo.py:177-178)
+    gives the same bits as the single-pass computation, for every descriptor, with bands shorter than the halo; a
+    numpy.memmap input takes that route by itself through the public API."""
+    from topo_descriptors_b200 import tiler
+
+    z = fractal_dem(700, 530, seed=21)
+    zi = np.rint(z).astype(np.float32)
+    res = {"x": np.full(530, 25.0), "y": np.full(700, -25.0)}
+    for dem in (z, zi):
+        assert np.array_equal(tiler.tpi(dem, 151, band_rows=90), topo.tpi(dem, 151))
+        assert np.array_equal(tiler.std(dem, 67, band_rows=200), topo.std(dem, 67))
+    assert np.array_equal(tiler.gauss(z, 40.0, band_rows=128), topo.dem(z, 40.0))
+    for sigma in (0.75, 3.25, 30.25):
+        for a, b in zip(tiler.gradient(z, sigma, res, band_rows=111), topo.gradient(z, sigma, res)):
+            assert np.array_equal(a, b), sigma
+    sw = tiler.sweep(zi, [9, 41, 151], band_rows=256)
+    for s in (9, 41, 151):
+        assert np.array_equal(sw[s][0], topo.tpi(zi, s)) and np.array_equal(sw[s][1], topo.std(zi, s)), s
+    n1, d1 = tiler.valley_ridge(z[:300], 9, "valley", band_rows=70)
+    n0, d0 = topo.valley_ridge(z[:300], 9, "valley")
+    assert np.array_equal(n1, n0) and np.array_equal(d1, d0)
+    ds = dem_dataset(z, res=25.0)
+    assert np.array_equal(tiler.sx(ds, [0.0, 135.0], 500.0, band_rows=100), topo.sx(ds, [0.0, 135.0], 500.0))
+    # a memory-mapped DEM goes out of core on its own
+    path = tmp_path / "dem.f32"
+    mm = np.memmap(path, dtype=np.float32, mode="w+", shape=z.shape)
+    mm[:] = z
+    mm.flush()
+    ro = np.memmap(path, dtype=np.float32, mode="r", shape=z.shape)
+    assert topo._out_of_core(ro) and np.array_equal(topo.tpi(ro, 33), topo.tpi(z, 33))
+
+
+def test_valley_ridge_fft_route_matches_the_oracle_and_the_direct_bank():
+    """Kernels from ~47 px up go through 2-D overlap-save FFT convolution (cost independent of the kernel size, like
+    the reference's own signal.convolve): same (norm, direction) as the float64 oracle -- closer than the direct float32
+    bank, the transforms are float64 -- at size 41 (forced), 81 and on a row band."""
+    z = fractal_dem(230, 300, seed=22)
+    old = dev.VALLEY_FFT_MIN_EXTENT
+    try:
+        for size in (41, 81):
+            wn, wd, gap = O.valley_ridge_exact(z, size, "valley", return_gap=True, direct_limit=0)
+            tol = max(TOL_M, 2e-6 * float(np.abs(wn).max()))
+            dev.VALLEY_FFT_MIN_EXTENT = 1
+            fn, fd = topo.valley_ridge(z, size, "valley")
+            assert maxdiff(fn, wn) <= tol, (size, maxdiff(fn, wn), tol)
+            decided = gap > 10 * tol
+            assert decided.mean() > 0.5 and np.array_equal(fd[decided], wd[decided]), size
+            if size == 41:
+                dev.VALLEY_FFT_MIN_EXTENT = 10**6
+                dn, dd = topo.valley_ridge(z, size, "valley")
+                assert maxdiff(fn, dn) <= 6e-6 * float(np.abs(wn).max())
+                assert np.array_equal(fd[decided], dd[decided])
+        # ridge, four flats (two channel groups on the direct route, 720 kernels here), a row band
+        dev.VALLEY_FFT_MIN_EXTENT = 1
+        flats = [0, 0.1, 0.2, 0.3, 0.4]
+        wn, wd, gap = O.valley_ridge_exact(z, 21, "ridge", flat_list=flats, return_gap=True, direct_limit=0)
+        fn, fd = topo.valley_ridge(z, 21, "ridge", flat_list=flats)
+        assert maxdiff(fn, wn) <= TOL_M and np.array_equal(fd[gap > 1e-2], wd[gap > 1e-2])
+        whole = DeviceDEM(dev.to_device(z))
+        st = whole.stats
+        mean = st["sum"] / st["n"]
+        normed = dev.zscore(whole, np.float32(mean), np.float32(np.sqrt(st["sumsq"] / st["n"] - mean * mean)))
+        bank = topo._device_bank(41, "valley", [0, 0.15, 0.3], whole.tensor.device)
+        ref_n, ref_d = dev.valley_ridge(normed, bank)
+        lo, hi, halo = 60, 170, bank["hmax"] // 2
+        band = DeviceDEM(normed.tensor[lo - halo : hi + halo].contiguous(), gny=230, gy0=lo - halo, stats=st)
+        bn, bd = dev.valley_ridge(band, bank, lo, hi - lo)
+        assert float((bn - ref_n[lo:hi]).abs().max()) <= 1e-3 and float((bd != ref_d[lo:hi]).float().mean()) <= 1e-3
+    finally:
+        dev.VALLEY_FFT_MIN_EXTENT = old
+
+
+def test_device_rotated_bank_equals_the_scipy_bank():
+    """the kernel bank rotated on the GPU (scipy's order-2 spline arithmetic restated, prefilter and
+    rotation set-up from scipy itself) against the host bank built by calling scipy.ndimage.rotate 180 times: identical
+    supports (zeros), values to float32 rounding (the z-score statistics are reduced in another order)."""
+    import torch
+
+    from topo_descriptors_b200 import _geometry as geo
+
+    for size, mode, flats in ((21, "valley", [0, 0.15, 0.3]), (41, "ridge", [0, 0.2])):
+        host = geo.build_valley_bank(size, mode, flats)["plain"]
+        bank = topo._device_bank_rotated_on_device(size, mode, flats, torch.device("cuda"))
+        got = bank["plain"]
+        assert np.array_equal(got["off"], host["off"]) and np.array_equal(got["hw"], host["hw"])
+        data = got["data"].cpu().numpy()
+        assert np.array_equal(data == 0, host["data"] == 0)
+        assert float(np.abs(data - host["data"]).max()) <= 2e-6 * float(np.abs(host["data"]).max())
+        assert np.mean(data != host["data"]) <= 0.05

@@ -3,6 +3,7 @@ Dataset duck-types, output names, and the C-ABI library's symbol table."""
 
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -376,3 +377,44 @@ def test_disc_queries_agree_with_the_plan_over_a_size_x_range_grid():
     # a cache laid out for a split square holds one more plane region
     base = lib.topo_disc_cache_bytes(vp, 801, 1, 200.0, 3400.0)
     assert base > 0 and lib.topo_disc_cache_bytes(vp, 801, 1, 0.0, 4800.0) * 2 == base * 3
+
+
+def test_tiler_band_plan_and_stats_merge():
+    from topo_descriptors_b200 import tiler
+
+    plan = tiler.band_plan(1000, 40, 300)
+    assert plan == [(0, 300, 0, 340), (300, 600, 260, 640), (600, 900, 560, 940), (900, 1000, 860, 1000)]
+    assert tiler.band_plan(10, 400, 4) == [(0, 4, 0, 10), (4, 8, 0, 10), (8, 10, 0, 10)]  # halo wider than the image
+    with pytest.raises(ValueError):
+        tiler.band_plan(10, 1, 0)
+    a = {"min": 1.0, "max": 5.0, "nonfinite": 0, "nonint": 2, "sum": 10.0, "sumsq": 30.0, "n": 4}
+    b = {"min": -2.0, "max": 3.0, "nonfinite": 1, "nonint": 0, "sum": 1.0, "sumsq": 5.0, "n": 3}
+    m = tiler.merge_stats([a, b])
+    assert m == {"min": -2.0, "max": 5.0, "nonfinite": 1, "nonint": 2, "sum": 11.0, "sumsq": 35.0, "n": 7}
+    assert not topo._out_of_core(np.zeros((4, 4), np.float32))
+
+
+def test_rotation_plan_equals_scipy_rotate_setup():
+    """_geometry.plan_rotations restates the set-up of scipy.ndimage.rotate(reshape=True): same output boxes as scipy for
+    every angle; profiles/proto/rotate_restated.py (run on CPU) shows the full restatement -- coordinates, quadratic
+    B-spline weights, mirrored taps -- bit-identical to scipy, which is what csrc/rotate.cu executes."""
+    from scipy import ndimage
+
+    from topo_descriptors_b200 import _geometry as geo
+
+    k = geo.valley_kernels(21, [0, 0.3])
+    angles = np.arange(0, 180, dtype=np.float32)
+    recs, total = geo.plan_rotations(k.shape[1:], k.shape[0], angles)
+    assert recs.dtype.itemsize == 64
+    pos = 0
+    for r, angle in zip(recs, angles):
+        want = ndimage.rotate(k, angle, axes=(1, 2), reshape=True, order=2, mode="constant", cval=-9999)
+        assert (int(r["oh"]), int(r["ow"])) == want.shape[1:] and int(r["out_off"]) == pos
+        pos += want.size
+    assert pos == total
+    sys.path.insert(0, os.path.join(ROOT, "profiles", "proto"))
+    import rotate_restated
+
+    for angle in (0.0, 17.0, 45.0, 90.0, 133.0):
+        want = ndimage.rotate(k, angle, axes=(1, 2), reshape=True, order=2, mode="constant", cval=-9999)
+        assert np.array_equal(rotate_restated.rotate_restated(k, angle), want)

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libtopo_b200.so")
-SOURCES = ["core.cu", "disc.cu", "gauss.cu", "gauss_fft.cu", "sx.cu", "valley.cu", "prestage.cu"]
+SOURCES = ["core.cu", "disc.cu", "gauss.cu", "gauss_fft.cu", "valley_fft.cu", "rotate.cu", "sx.cu", "valley.cu", "prestage.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -31,6 +31,7 @@ def needs_build():
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [
         os.path.join(CSRC, "common.cuh"),
         os.path.join(CSRC, "tma.cuh"),
+        os.path.join(CSRC, "fft_smem.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "topo_b200.h"),
     ]
     return any(os.path.getmtime(d) > t for d in deps)

@@ -113,6 +113,43 @@ def rotate_kernels(kernels, angle):
     return out
 
 
+ROT_ANGLE_DTYPE = np.dtype([("m", np.float64, (4,)), ("off", np.float64, (2,)), ("out_off", np.int64), ("oh", np.int32),
+                            ("ow", np.int32)])  # 64 bytes: `RotAngle` of csrc/rotate.cu
+
+
+def plan_rotations(shape_hw, n_kernels, angles):
+    """What ``scipy.ndimage.rotate(reshape=True)`` computes before it interpolates (scipy/ndimage/_interpolation.py):
+    rotation matrix from cosdg / sindg, output box, offset -- for every angle, plus the element offset of the angle's
+    ``[n_kernels][oh][ow]`` block.  Returns (records, total elements)."""
+    from scipy import special
+
+    recs = np.zeros(len(angles), dtype=ROT_ANGLE_DTYPE)
+    iy, ix = (int(v) for v in shape_hw)
+    pos = 0
+    for r, angle in zip(recs, angles):
+        c, s = special.cosdg(angle), special.sindg(angle)
+        rot = np.array([[c, s], [-s, c]])
+        out_bounds = rot @ [[0, 0, iy, iy], [0, ix, 0, ix]]
+        out_shape = (np.ptp(out_bounds, axis=1) + 0.5).astype(int)
+        out_center = rot @ ((out_shape - 1) / 2)
+        offset = (np.array([iy, ix]) - 1) / 2 - out_center
+        r["m"] = rot.ravel()
+        r["off"] = offset
+        r["out_off"] = pos
+        r["oh"], r["ow"] = out_shape
+        pos += int(n_kernels) * int(out_shape[0]) * int(out_shape[1])
+    return recs, pos
+
+
+def spline_coefficients(kernels):
+    """Quadratic-spline prefilter of the source kernels, exactly as ``ndimage.rotate(order=2, mode="constant")`` applies
+    it (angle independent; float64)."""
+    from scipy import ndimage
+
+    return np.stack([ndimage.spline_filter(np.asarray(k, dtype=np.float64), order=2, output=np.float64, mode="constant")
+                     for k in kernels])
+
+
 def mix_channels(kernels_rot):
     """What the reference's 3-D ``signal.convolve(dem3d, kernels_rot, "same")`` (topo.py:431,443)
     applies per output channel: the DEM is broadcast along the flat-list axis, so the convolution
@@ -146,9 +183,27 @@ def build_valley_bank(size, mode, flat_list, angles=None, rotate=None):
     mixed_all = [mix_channels(rotate(base, ang)) for ang in angles]
     if base.shape[0] > 4:
         groups = [_pack_bank([m[c : c + 4] for m in mixed_all]) for c in range(0, base.shape[0], 4)]
-        return {"groups": groups, "n_angles": len(mixed_all), "n_ch": base.shape[0],
+        bank = {"groups": groups, "n_angles": len(mixed_all), "n_ch": base.shape[0],
                 "hmax": max(g["hmax"] for g in groups), "wmax": max(g["wmax"] for g in groups)}
-    return _pack_bank(mixed_all)
+    else:
+        bank = _pack_bank(mixed_all)
+    bank["plain"] = _plain_bank(mixed_all)
+    return bank
+
+
+def _plain_bank(mixed_all):
+    """The same kernels for the FFT route (``topo_valley_ridge_fft_f32``): scipy's orientation (not flipped), row-major,
+    concatenated in angle order; per kernel its element offset and (h, w, angle index)."""
+    flat, off, hw = [], [], []
+    pos = 0
+    for a, mixed in enumerate(mixed_all):
+        for m in range(mixed.shape[0]):
+            k = np.ascontiguousarray(mixed[m], dtype=np.float32)
+            flat.append(k.ravel())
+            off.append(pos)
+            hw.append((k.shape[0], k.shape[1], a))
+            pos += k.size
+    return {"data": np.concatenate(flat), "off": np.array(off, dtype=np.int64), "hw": np.array(hw, dtype=np.int32)}
 
 
 def _pack_bank(mixed_all):

@@ -78,6 +78,10 @@ PROTOTYPES = {
     "topo_nan_indices_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
     "topo_zscore_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_float, c_void_p]),
+    "topo_rotate_bank_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "topo_valley_ridge_fft_workspace_bytes": (c_size_t, [_VP, c_int, c_int]),
+    "topo_valley_ridge_fft_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, _VP, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "topo_valley_ridge_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, _VP, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }

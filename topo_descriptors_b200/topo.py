@@ -62,6 +62,18 @@ class _Marshal:
         return arr
 
 
+def _out_of_core(dem):
+    """True for inputs that should be streamed through HBM in row bands instead of being uploaded whole: a
+    ``numpy.memmap``, a dask array (the reference's ``map_overlap`` case, topo.py:177-178) or a DataArray backed by
+    one.  Such inputs go through :mod:`tiler` (same kernels, global-coordinate views, bit-identical results)."""
+    data = dem.data if _xr.is_dataarray(dem) and not isinstance(dem, _xr.DataArray) else dem
+    return isinstance(data, np.memmap) or (hasattr(data, "chunks") and hasattr(data, "compute"))
+
+
+def _lazy_source(dem):
+    return dem.data if _xr.is_dataarray(dem) and not isinstance(dem, _xr.DataArray) else dem
+
+
 def _smoothed(ddem, sigma):
     """Optional Gaussian pre-smoothing (topo.py:172-173, 297-298, 426-427).  The smoothed surface is
     a new DEM: its statistics (range, integrality) are recomputed."""
@@ -94,6 +106,10 @@ def compute_dem(dem_ds, scales, ind_nans=[], crop=None, outdir="."):
 
 def dem(dem, sigma):
     """Gaussian-smoothed DEM, ``scipy.ndimage.gaussian_filter(dem, sigma)`` semantics (topo.py:62-80)."""
+    if _out_of_core(dem):
+        from . import tiler
+
+        return tiler.gauss(_lazy_source(dem), sigma)
     m = _Marshal(dem)
     sig = (sigma, sigma) if np.isscalar(sigma) else tuple(sigma)
     return m.back(dev.gauss(m.ddem, sig[0], sig[1]))
@@ -142,6 +158,11 @@ def tpi(dem, size, sigma=None):
     size follows the FFT rule (all NaN), which is what the compute_* drivers assume when they re-stamp ``ind_nans``
     on a filled DEM.
     """
+    if _out_of_core(dem):
+        from . import tiler
+
+        src = _lazy_source(dem)
+        return tiler.tpi(tiler.gauss(src, sigma) if sigma else src, int(size))
     m = _Marshal(dem)
     return m.back(dev.tpi(_smoothed(m.ddem, sigma), int(size)))
 
@@ -193,6 +214,11 @@ def std(dem, size, sigma=None):
     kernel computes the variance in exact integer / float64 arithmetic and stores float32).
     float64 DEMs are rounded to float32 on upload (see ``tpi``); non-finite input gives an all-NaN result.
     """
+    if _out_of_core(dem):
+        from . import tiler
+
+        src = _lazy_source(dem)
+        return tiler.std(tiler.gauss(src, sigma) if sigma else src, int(size))
     m = _Marshal(dem)
     return m.back(dev.std(_smoothed(m.ddem, sigma), int(size)), dtype=np.float64)
 
@@ -230,9 +256,45 @@ def compute_valley_ridge(dem_ds, scales, mode, flat_list=[0, 0.15, 0.3], smth_fa
 _BANK_CACHE = {}
 
 
+def _device_bank_rotated_on_device(size, mode, flat_list, device):
+    """The bank of the FFT route for large kernels, rotated on the GPU: the host only runs scipy's
+    spline prefilter on the F source kernels and the 180 rotation set-ups."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+
+    base = geo.valley_kernels(int(size), list(flat_list))
+    if mode == "ridge":
+        base = base * np.float32(-1)
+    F, H, W = base.shape
+    angles = np.arange(0, 180, dtype=np.float32)
+    recs, total = geo.plan_rotations((H, W), F, angles)
+    coef = torch.from_numpy(geo.spline_coefficients(base)).to(device)
+    recs_dev = torch.from_numpy(recs.view(np.uint8).reshape(-1).copy()).to(device)
+    scratch = torch.empty(total, dtype=torch.float32, device=device)
+    out = torch.empty(total, dtype=torch.float32, device=device)
+    _lib.call("topo_rotate_bank_f32", dev._ptr(coef), F, H, W, dev._ptr(recs_dev), len(recs), ctypes.c_float(-9999.0),
+              dev._ptr(scratch), dev._ptr(out), dev._stream())
+    off, hw = [], []
+    for a, r in enumerate(recs):
+        n = int(r["oh"]) * int(r["ow"])
+        for m in range(F):
+            off.append(int(r["out_off"]) + m * n)
+            hw.append((int(r["oh"]), int(r["ow"]), a))
+    return {"plain": {"data": out, "off": np.array(off, dtype=np.int64), "hw": np.array(hw, dtype=np.int32)},
+            "n_angles": len(recs), "n_ch": F, "hmax": int(recs["oh"].max()), "wmax": int(recs["ow"].max())}
+
+
 def _device_bank(size, mode, flat_list, device):
     key = (int(size), mode, tuple(float(f) for f in flat_list), str(device))
     bank = _BANK_CACHE.get(key)
+    if bank is None and int(size) * 1.42 >= dev.VALLEY_FFT_MIN_EXTENT and dev.VALLEY_DEVICE_ROTATION:
+        bank = _device_bank_rotated_on_device(size, mode, flat_list, device)
+        if len(_BANK_CACHE) > 16:
+            _BANK_CACHE.clear()
+        _BANK_CACHE[key] = bank
     if bank is None:
         import torch
 
@@ -245,6 +307,8 @@ def _device_bank(size, mode, flat_list, device):
             return b
 
         bank = dict(host, groups=[upload(g) for g in host["groups"]]) if "groups" in host else upload(host)
+        plain = host["plain"]  # FFT route: kernels on the device, offsets / extents stay on the host
+        bank["plain"] = {"data": torch.from_numpy(plain["data"]).to(device), "off": plain["off"], "hw": plain["hw"]}
         if len(_BANK_CACHE) > 16:
             _BANK_CACHE.clear()
         _BANK_CACHE[key] = bank
@@ -333,6 +397,10 @@ def gradient(dem, sigma, res_meters, sig_ratio=1):
     second return value of ``helpers.scale_to_pixel``); slope in degrees, aspect clockwise from
     north.  float32, evaluated in the reference's own operation order.
     """
+    if _out_of_core(dem) and sig_ratio == 1:
+        from . import tiler
+
+        return tiler.gradient(_lazy_source(dem), sigma, res_meters)
     m = _Marshal(dem)
     d = m.ddem
     device = d.tensor.device
