@@ -485,16 +485,30 @@ def run_gpu(args, rank, world, local_rank):
         bank = topo._device_bank(C5_KSIZE, "valley", flats, device)  # bank build is setup, cached per (size, mode, flats)
         ms_v, _ = timed_steps(lambda: bands.valley_ridge_band(core5, ctx5, C5_KSIZE, "valley", flats), 1, 1)
         ms_s, _ = timed_steps(lambda: bands.sx_band(core5, ctx5, plan5, 10.0), 1, 3)
-        macs = float(sum(int(h) * int(w) for h, w, _, _ in bank["hw"].cpu().numpy())) * bank["n_ch"]
+        macs = float(sum(int(h) * int(w) for h, w, _a in bank["plain"]["hw"]))  # taps of all 180 x F mixed kernels
         tfma = macs * n5 * n5 / (ms_v * 1e-3) / 1e12
-        fma_peak = 128.0 * 148 * world * clk / 1e12
+        fft_route = max(int(bank["hmax"]), int(bank["wmax"])) >= dev.VALLEY_FFT_MIN_EXTENT
+        if fft_route:
+            # FFT route: per kernel pair and 2048^2 tile the product + inverse pass reads two spectra and writes one plane,
+            # the transpose moves it once more, the fold reads it: 6 planes of 16 B x T^2
+            T = 2048
+            v_out = T - int(bank["hmax"]) + 1
+            planes = (-(-ctx5.rows // v_out)) * (-(-n5 // (T - int(bank["wmax"]) + 1)))
+            pairs = (len(bank["plain"]["hw"]) + 1) // 2
+            gbs = pairs * planes * 6 * 16.0 * T * T / (ms_v * 1e-3) / 1e9
+            v_roof = {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak(), "unit": "GB/s", "frac": round(gbs / hbm_peak(), 3),
+                      "note": f"2-D overlap-save FFT route: {pairs} kernel pairs x {planes} tiles of {T}^2 float64 complex, 6 plane "
+                              f"transfers each; dense-equivalent bank rate {tfma:.1f} TFMA/s (fp32 FMA peak {128.0 * 148 * world * clk / 1e12:.1f})"}
+        else:
+            fma_peak = 128.0 * 148 * world * clk / 1e12
+            v_roof = {"bound": "fp32 fma", "achieved": round(tfma, 2), "peak": round(fma_peak, 1),
+                      "unit": "TFMA/s (dense-equivalent bank taps)", "frac": round(tfma / fma_peak, 3)}
         extra["config5"] = {
             "workload": f"config 5 kernels on a {n5}x{n5} {RES_M:g} m DEM in {world} row band(s) (the full 32768^2 runs through bench_c5.py): "
                         f"valley_ridge size {C5_KSIZE} (180 angles x 3 flats) and Sx radius {C5_RADIUS:g} m (window {plan5[3]} px, "
                         f"{int(plan5[2][-1])} samples)",
             "valley_ridge": {"ms": round(ms_v, 2), "value": round(n5 * n5 / (ms_v * 1e-3) / 1e6, 2), "unit": "Mpixel/s",
-                             "roofline": {"bound": "fp32 fma", "achieved": round(tfma, 2), "peak": round(fma_peak, 1),
-                                          "unit": "TFMA/s (dense-equivalent bank taps)", "frac": round(tfma / fma_peak, 3)}},
+                             "route": "fft" if fft_route else "direct", "roofline": v_roof},
             "sx_10km": {"ms": round(ms_s, 2), "value": round(n5 * n5 / (ms_s * 1e-3) / 1e6, 1), "unit": "Mpixel/s"},
             "scaling": "strong",
         }
@@ -613,6 +627,11 @@ def run_gpu(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(path))["hbm_gbs"]) if os.path.exists(path) else 6650.0
 
 
 def band_spot_check(core, ctx, sizes, sigmas, res_x, res_y, rank, device):

@@ -76,7 +76,7 @@ def main():
     ms_sx = timed(lambda: bands.sx_band(core, ctx, plan, 10.0))
     if rank == 0:
         px = float(n) * n
-        macs = float(sum(int(h) * int(w) for h, w, _, _ in bank["hw"].cpu().numpy())) * bank["n_ch"]
+        macs = float(sum(int(h) * int(w) for h, w, _a in bank["plain"]["hw"]))
         print(json.dumps({
             "config": f"config 5: {n}x{n} 25 m DEM, valley_ridge size {args.ksize} (180 angles x 3 flats) + Sx radius "
                       f"{args.radius:.0f} m (window {plan[3]} px, {int(plan[2][-1])} samples), row bands x{world}",

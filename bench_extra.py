@@ -135,7 +135,7 @@ def main():
         bank = topo._device_bank(size, "valley", [0, 0.15, 0.3], d5.tensor.device)
         bank_s = time.perf_counter() - t0
         ms = timed(lambda: dev.valley_ridge(normed, bank), reps=3)
-        macs = float(sum(int(h) * int(w) for h, w, _, _ in bank["hw"].cpu().numpy())) * bank["n_ch"]
+        macs = float(sum(int(h) * int(w) for h, w, _a in bank["plain"]["hw"]))
         add("C5", f"valley_ridge size {size}, 180 angles x 3 flats, {n5}^2 crop", n5 * n5, ms,
             note=f"{macs:.0f} MAC/px -> {macs * n5 * n5 / ms / 1e9:.2f} TFMA/s fp32; bank build {bank_s:.2f} s (host, cached)")
     ds5 = dem_dataset(z5, res=25.0)

@@ -281,6 +281,7 @@ def test_valley_ridge_fft_route_matches_the_oracle_and_the_direct_bank():
             assert decided.mean() > 0.5 and np.array_equal(fd[decided], wd[decided]), size
             if size == 41:
                 dev.VALLEY_FFT_MIN_EXTENT = 10**6
+                topo._BANK_CACHE.clear()  # the cached bank was rotated on the device: FFT layout only
                 dn, dd = topo.valley_ridge(z, size, "valley")
                 assert maxdiff(fn, dn) <= 6e-6 * float(np.abs(wn).max())
                 assert np.array_equal(fd[decided], dd[decided])
@@ -290,6 +291,7 @@ def test_valley_ridge_fft_route_matches_the_oracle_and_the_direct_bank():
         wn, wd, gap = O.valley_ridge_exact(z, 21, "ridge", flat_list=flats, return_gap=True, direct_limit=0)
         fn, fd = topo.valley_ridge(z, 21, "ridge", flat_list=flats)
         assert maxdiff(fn, wn) <= TOL_M and np.array_equal(fd[gap > 1e-2], wd[gap > 1e-2])
+        topo._BANK_CACHE.clear()
         whole = DeviceDEM(dev.to_device(z))
         st = whole.stats
         mean = st["sum"] / st["n"]
@@ -302,6 +304,7 @@ def test_valley_ridge_fft_route_matches_the_oracle_and_the_direct_bank():
         assert float((bn - ref_n[lo:hi]).abs().max()) <= 1e-3 and float((bd != ref_d[lo:hi]).float().mean()) <= 1e-3
     finally:
         dev.VALLEY_FFT_MIN_EXTENT = old
+        topo._BANK_CACHE.clear()
 
 
 def test_device_rotated_bank_equals_the_scipy_bank():

@@ -463,7 +463,8 @@ def valley_ridge(dem_norm, bank, out_gy0=None, out_rows=None):
     """Running (max, argmax) over the rotated-kernel bank -> (norm, dir) tensors.  ``bank``: one packed bank, or a dict
     whose ``"groups"`` lists several (flat lists longer than 4 run in groups of 4 channels sharing the running maximum)."""
     require_cuda()
-    if "plain" in bank and max(int(bank["hmax"]), int(bank["wmax"])) >= VALLEY_FFT_MIN_EXTENT:
+    packed = "data" in bank or "groups" in bank  # a bank rotated on the device only has the FFT route's layout
+    if "plain" in bank and (not packed or max(int(bank["hmax"]), int(bank["wmax"])) >= VALLEY_FFT_MIN_EXTENT):
         return valley_ridge_fft(dem_norm, bank, out_gy0, out_rows)
     v = dem_norm.view(out_gy0, out_rows)
     norm = _new(v.out_rows, dem_norm.nx, dem_norm.tensor)
