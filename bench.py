@@ -381,6 +381,30 @@ def run_gpu(args, rank, world, local_rank):
     # ---- e2e: host (pinned) -> HBM -> sweep -> every output back to the host, per step.  The D2H copies run
     # on a second stream into a ring of pinned buffers so that PCIe traffic overlaps the kernels; the compute
     # stream is throttled to at most `kInFlight` outputs waiting for their copy.
+    # N > 1: this leg is bound by getting 60 GiB of results off the GPUs, and the ranks do not drain at the same rate
+    # when all copy at once (measured on this box class: 12.1 GB/s for GPUs 0-3, 18.1 GB/s for GPUs 4-7, 121 GB/s in
+    # total, against 56 GB/s for one GPU alone: profiles/r02_d2h_probe_n8.json) -- so the bands of this leg are sized in
+    # proportion to each rank's concurrent device -> host rate, probed here with a 256 MiB copy
+    ctx_dev, host_dev = ctx, host
+    d2h_rates = None
+    if world > 1:
+        probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+        probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        probe_h.copy_(probe_d, non_blocking=True)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(4):
+            probe_h.copy_(probe_d, non_blocking=True)
+        q1.record()
+        torch.cuda.synchronize()
+        rate = torch.tensor([4 * (256 << 20) / (q0.elapsed_time(q1) * 1e-3) / 1e9], dtype=torch.float64, device=device)
+        rates = [torch.zeros_like(rate) for _ in range(world)]
+        dist.all_gather(rates, rate)
+        d2h_rates = [round(float(r.item()), 1) for r in rates]
+        del probe_d, probe_h
+        ctx = bands.BandContext(ny, nx, rank, world, weights=d2h_rates)
+        host = torch.from_numpy(make_dem_rows(ny, nx, ctx.r0, ctx.r1, integer=False)).pin_memory()
     kInFlight = 6
     pinned_ring = [torch.empty((ctx.rows, nx), dtype=torch.float32).pin_memory() for _ in range(3)]
     copy_stream = torch.cuda.Stream(device=device)
@@ -419,8 +443,13 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
     e2e_value = n_calls * ny * nx / (e2e_ms / e2e_steps * 1e-3) / 1e6
-    e2e_d2h = int(d2h[0] // e2e_steps)
+    e2e_d2h = torch.tensor([float(d2h[0] // e2e_steps), float(ctx.rows * nx * 4)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_d2h)  # bytes of the whole job
+    e2e_d2h, e2e_h2d = int(e2e_d2h[0].item()), int(e2e_d2h[1].item())
+    e2e_rows = [p[1] - p[0] for p in ctx.parts]
     del pinned_ring
+    ctx, host = ctx_dev, host_dev
 
     # ---- N > 1: the bands of this very run against an independent whole-image-coordinates strip (bit for bit)
     band_check = None
@@ -593,8 +622,8 @@ def run_gpu(args, rank, world, local_rank):
         "config": dict(workload_config(ny, nx, sizes, "float"),
                        parallelism=f"row bands x{world}, halo exchange over NVLink", numa_bound=bool(numa_bound)),
         "clocks": clocks.summary(),
-        "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": int(ctx.rows * nx * 4),
-                "d2h_bytes_per_step": e2e_d2h, "steps": e2e_steps,
+        "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": e2e_h2d,
+                "d2h_bytes_per_step": e2e_d2h, "steps": e2e_steps, "band_rows": e2e_rows, "d2h_GBps_all_ranks_at_once": d2h_rates,
                 "path": "pinned host DEM -> HBM -> bands.sweep -> every output band back to pinned host memory (D2H on a second stream, overlapped)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
@@ -671,7 +700,7 @@ def band_spot_check(core, ctx, sizes, sigmas, res_x, res_y, rank, device):
         a, b = max(0, edge - H - halo), min(ctx.gny, edge + H + halo)
         band = torch.from_numpy(make_dem_rows(ctx.gny, ctx.nx, a, b, integer=False)).to(device)
         d = DeviceDEM(band, gny=ctx.gny, gy0=a, stats=stats).share_disc_planes(size)
-        want = {"tpi": dev.tpi(d, size, edge - H, 2 * H), "std": dev.std(d, size, edge - H, 2 * H)}
+        want = {"tpi": dev.tpi(d, size, edge - H, 2 * H, pair_std=True), "std": dev.std(d, size, edge - H, 2 * H)}
         d.release_disc_planes()
         g0 = edge - H - 1
         g = DeviceDEM(dev.gauss(d, sigmas[gi], sigmas[gi], g0, 2 * H + 2), gny=ctx.gny, gy0=g0, stats=stats)

@@ -41,7 +41,7 @@ def main():
         # fixed-point scale of the largest size), so the whole-image reference runs it too
         whole.share_disc_planes(max(sizes))
         for i, size in enumerate(sizes):
-            ref = {"tpi": dev.tpi(whole, size), "std": dev.std(whole, size)}
+            ref = {"tpi": dev.tpi(whole, size, pair_std=True), "std": dev.std(whole, size)}
             g = DeviceDEM(dev.gauss(whole, sigmas[i], sigmas[i]))
             outs = dev.gradient_from_smooth(g, g, rx[0], 0, ry[0], 0)
             ref.update(dict(zip(("dx", "dy", "slope", "aspect"), outs)))

@@ -23,6 +23,13 @@ def test_partition_rows():
         p = np.array(parts)
         sizes = p[:, 1] - p[:, 0]
         assert sizes.max() - sizes.min() <= 1
+    # weighted bands (e.g. by measured D2H rate): proportional, contiguous, at least one row each
+    assert bands.partition_rows(100, 4, [2, 2, 3, 3]) == [(0, 20), (20, 40), (40, 70), (70, 100)]
+    assert bands.partition_rows(5, 4, [0, 0, 1, 0]) == [(0, 1), (1, 2), (2, 4), (4, 5)]
+    w = [12.1] * 4 + [18.1] * 4
+    parts = bands.partition_rows(16384, 8, w)
+    assert parts[0][0] == 0 and parts[-1][1] == 16384 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    assert abs((parts[7][1] - parts[7][0]) / (parts[0][1] - parts[0][0]) - 18.1 / 12.1) < 0.01
     ctx = bands.BandContext(100, 8, rank=1, world=4)
     assert (ctx.r0, ctx.r1, ctx.rows) == (25, 50, 25)
     assert ctx.halo_extent(10) == (15, 60) and bands.BandContext(100, 8, 0, 4).halo_extent(10) == (0, 35)

@@ -15,8 +15,22 @@ The reference's own precedent is ``dask.array.map_overlap(depth=2*size)`` in ``t
 import numpy as np
 
 
-def partition_rows(gny, world):
-    """Balanced contiguous row ranges: [(r0, r1)] * world (first ``gny % world`` ranks get one more)."""
+def partition_rows(gny, world, weights=None):
+    """Contiguous row ranges [(r0, r1)] * world.  Balanced by default (the first ``gny % world`` ranks get one more
+    row); with ``weights`` the bands are proportional to them (e.g. to each rank's measured device -> host rate when the
+    job is bound by getting the results off the GPUs), every rank keeping at least one row."""
+    if weights is not None:
+        w = np.maximum(np.asarray(weights, dtype=np.float64), 0.0)
+        if len(w) != int(world) or not np.isfinite(w).all() or w.sum() <= 0:
+            raise ValueError("weights must be one non-negative finite number per rank")
+        edges = np.rint(np.cumsum(w) / w.sum() * int(gny)).astype(np.int64)
+        edges[-1] = int(gny)
+        out, r = [], 0
+        for k in range(int(world)):
+            e = int(min(max(edges[k], r + 1), int(gny) - (int(world) - 1 - k)))
+            out.append((r, e))
+            r = e
+        return out
     base, extra = divmod(int(gny), int(world))
     out, r = [], 0
     for k in range(world):
@@ -29,9 +43,9 @@ def partition_rows(gny, world):
 class BandContext:
     """Where this rank sits in the row-band decomposition."""
 
-    def __init__(self, gny, nx, rank=0, world=1):
+    def __init__(self, gny, nx, rank=0, world=1, weights=None):
         self.gny, self.nx, self.rank, self.world = int(gny), int(nx), int(rank), int(world)
-        self.parts = partition_rows(gny, world)
+        self.parts = partition_rows(gny, world, weights)
         self.r0, self.r1 = self.parts[rank]
 
     @property
@@ -89,16 +103,15 @@ def global_stats(local, ctx, device=None):
     import torch.distributed as dist
 
     dev = device if device is not None else "cpu"
-    mn = torch.tensor([local["min"]], dtype=torch.float64, device=dev)
-    mx = torch.tensor([local["max"]], dtype=torch.float64, device=dev)
+    # two collectives and ONE device -> host read: (-min, max) under MAX, the counts and sums under SUM
+    ext = torch.tensor([-local["min"], local["max"]], dtype=torch.float64, device=dev)
     sm = torch.tensor([local["nonfinite"], local["nonint"], local["sum"], local["sumsq"], local["n"]],
                       dtype=torch.float64, device=dev)
-    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ext, op=dist.ReduceOp.MAX)
     dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-    sm = sm.cpu().numpy()
-    return {"min": float(mn.item()), "max": float(mx.item()), "nonfinite": int(sm[0]), "nonint": int(sm[1]),
-            "sum": float(sm[2]), "sumsq": float(sm[3]), "n": int(sm[4])}
+    out = torch.cat([ext, sm]).cpu().numpy()
+    return {"min": float(-out[0]), "max": float(out[1]), "nonfinite": int(out[2]), "nonint": int(out[3]),
+            "sum": float(out[4]), "sumsq": float(out[5]), "n": int(out[6])}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -137,7 +150,9 @@ def sweep(core, ctx, sizes, sigmas, res_x, res_y, what=("tpi", "std", "gradient"
     calls = 0
     rx, rx2d = res_x
     ry, ry2d = res_y
-    for i, size in enumerate(sizes):
+    # largest scales first: their kernels run for milliseconds, so the host gets ahead of the GPU right after the
+    # statistics read-back instead of feeding it one short launch at a time (matters on thin bands: 8 GPUs)
+    for i, size in sorted(enumerate(sizes), key=lambda e: -int(e[1])):
         if "tpi" in what:
             out = dev.tpi(ddem, size, ctx.r0, ctx.rows, pair_std="std" in what)
             calls += 1
@@ -150,7 +165,7 @@ def sweep(core, ctx, sizes, sigmas, res_x, res_y, what=("tpi", "std", "gradient"
                 sink("std", i, out)
     ddem.release_disc_planes()
     if "gradient" in what:
-        for i, sigma in enumerate(sigmas):
+        for i, sigma in sorted(enumerate(sigmas), key=lambda e: -float(e[1])):
             if sigma <= 1:
                 outs = dev.sobel_gradient(ddem, rx, rx2d, ry, ry2d, True, ctx.r0, ctx.rows)
             else:
