@@ -324,3 +324,27 @@ def test_device_rotated_bank_equals_the_scipy_bank():
         assert np.array_equal(data == 0, host["data"] == 0)
         assert float(np.abs(data - host["data"]).max()) <= 2e-6 * float(np.abs(host["data"]).max())
         assert np.mean(data != host["data"]) <= 0.05
+
+
+def test_sweep_graph_replay_equals_the_eager_sweep():
+    """bands.SweepGraph captures the kernel sequence of a sweep once and replays it: same bits as the eager sweep, also
+    on the second replay and after the DEM changed (same statistics key -> same graph; different range -> re-capture)."""
+    import torch
+
+    from topo_descriptors_b200 import bands
+
+    sizes, sigmas = [5, 21, 67, 151], [1.25, 5.25, 16.75, 37.75]
+    z = fractal_dem(400, 520, seed=23)
+    ctx = bands.BandContext(400, 520)
+    rx = (dev._Res(np.full(520, 25.0), torch.device("cuda")), 0)
+    ry = (dev._Res(np.full(400, -25.0), torch.device("cuda")), 0)
+    sg = bands.SweepGraph(keep=True)
+    for k, dem in enumerate((z, z, z[::-1].copy(), z * np.float32(0.5))):
+        core = torch.from_numpy(np.ascontiguousarray(dem)).cuda()
+        want = {}
+        bands.sweep(core, ctx, sizes, sigmas, rx, ry, sink=lambda n, i, t: want.__setitem__((n, i), t.clone()))
+        sg.run(core, ctx, sizes, sigmas, rx, ry)
+        torch.cuda.synchronize()
+        assert set(sg.outputs) == set(want) and sg.launches > 50
+        for key, w in want.items():
+            assert torch.equal(sg.outputs[key], w), (k, key)

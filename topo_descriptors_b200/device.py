@@ -306,7 +306,7 @@ def _plane_cache(dem, v, size, st):
         return None
     nbytes = _lib.load().topo_disc_cache_bytes(ctypes.byref(v), int(hint), 1 if st["nonint"] == 0 else 0, st["min"],
                                                st["max"])
-    if nbytes == 0 or not _fits_in_hbm(2 * nbytes, dem.tensor.device):
+    if nbytes == 0 or not (getattr(dem, "_assume_fits", False) or _fits_in_hbm(2 * nbytes, dem.tensor.device)):
         return None  # (a DEM too large for shared planes runs every size on its own workspace, as without the hint)
     mem = _torch().empty(nbytes + 256, dtype=_torch().uint8, device=dem.tensor.device)
     base = (mem.data_ptr() + 255) & ~255
