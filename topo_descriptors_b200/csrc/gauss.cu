@@ -125,20 +125,41 @@ __global__ void __launch_bounds__(256, 2) gauss_axis0_kernel(const GaussParams p
     }
 }
 
-// 32 x 32 tiled transpose (rows x cols -> cols x rows); lets the wide-radius axis-1 pass reuse the
-// column kernel above at full lane occupancy.
+// 64 x 64 tiled transpose (rows x cols -> cols x rows); lets the wide-radius passes along y run on contiguous lines.
+// 128-bit loads along the rows, 128-bit stores along the transposed rows (each thread gathers a column quad from the
+// padded tile: conflict-free), edge tiles and unaligned rasters element by element.
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t ld_in,
                                                         float* __restrict__ out, int64_t ld_out, int rows, int cols) {
-    __shared__ float t[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        if (r < rows && c < cols) t[i][threadIdx.x] = __ldg(in + (int64_t)r * ld_in + c);
+    __shared__ float t[64][65];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const bool full = c0 + 64 <= cols && r0 + 64 <= rows && (ld_in & 3) == 0 && (ld_out & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (full) {
+        const int q = tid & 15, rr = tid >> 4;  // 16 quads per tile row, 16 rows per sweep
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = rr + 16 * i;
+            const float4 v = ldg4(in + (int64_t)(r0 + r) * ld_in + c0 + 4 * q);
+            t[r][4 * q] = v.x, t[r][4 * q + 1] = v.y, t[r][4 * q + 2] = v.z, t[r][4 * q + 3] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = rr + 16 * i;  // output row = input column
+            const float4 v = make_float4(t[4 * q][c], t[4 * q + 1][c], t[4 * q + 2][c], t[4 * q + 3][c]);
+            *reinterpret_cast<float4*>(out + (int64_t)(c0 + c) * ld_out + r0 + 4 * q) = v;
+        }
+        return;
+    }
+    for (int i = tid; i < 64 * 64; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        if (r0 + r < rows && c0 + c < cols) t[r][c] = __ldg(in + (int64_t)(r0 + r) * ld_in + c0 + c);
     }
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (c < cols && r < rows) out[(int64_t)c * ld_out + r] = t[threadIdx.x][i];
+    for (int i = tid; i < 64 * 64; i += 256) {
+        const int c = i >> 6, r = i & 63;
+        if (r0 + r < rows && c0 + c < cols) out[(int64_t)(c0 + c) * ld_out + r0 + r] = t[r][c];
     }
 }
 
@@ -766,12 +787,12 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
             // transpose the band, filter its lines (= the image columns) with the FFT pass, transpose back
             float* t1 = reinterpret_cast<float*>(wsb + L.t1);
             float* t2 = reinterpret_cast<float*>(wsb + L.t2);
-            dim3 tg(ceil_div(v->nx, 32), ceil_div(v->in_rows, 32));
+            dim3 tg(ceil_div(v->nx, 64), ceil_div(v->in_rows, 64));
             TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(in, ld_in, t1, tp_in, v->in_rows, v->nx));
             if (fft_conv_rows(t1, tp_in, t2, tp_out, v->nx, v->gny, v->in_gy0, v->in_rows, v->out_gy0, v->out_rows, w_y, lw_y,
                               wsb + L.tables, s))
                 return -1;
-            dim3 tg2(ceil_div(v->out_rows, 32), ceil_div(v->nx, 32));
+            dim3 tg2(ceil_div(v->out_rows, 64), ceil_div(v->nx, 64));
             TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg2, dim3(32, 8), 0, s>>>(t2, tp_out, dst, dst_ld, v->nx, v->out_rows));
         } else {
             GaussParams p{cur, dst, cur_ld, dst_ld, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_y, lw_y};
@@ -795,7 +816,7 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
         // wide radius, NaN-exact: transpose -> column kernel -> transpose back
         float* t1 = reinterpret_cast<float*>(wsb + L.t1);
         float* t2 = reinterpret_cast<float*>(wsb + L.t2);
-        dim3 tg(ceil_div(v->nx, 32), ceil_div(v->out_rows, 32));
+        dim3 tg(ceil_div(v->nx, 64), ceil_div(v->out_rows, 64));
         TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(src, cur_ld, t1, tp_out, v->out_rows, v->nx));
         GaussParams p{t1, t2, tp_out, tp_out, v->out_rows, v->nx, 0, v->nx, 0, v->nx, w_x, lw_x};
         dim3 grid(ceil_div(v->out_rows, kA0Cols), ceil_div(v->nx, 8 * kK));
@@ -805,7 +826,7 @@ int topo_gauss_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, c
             TOPO_LAUNCH("gauss_axis0<nansafe>", s, gauss_axis0_kernel<true><<<grid, dim3(32, 8), smem, s>>>(p));
         else
             TOPO_LAUNCH("gauss_axis0", s, gauss_axis0_kernel<false><<<grid, dim3(32, 8), smem, s>>>(p));
-        dim3 tg2(ceil_div(v->out_rows, 32), ceil_div(v->nx, 32));
+        dim3 tg2(ceil_div(v->out_rows, 64), ceil_div(v->nx, 64));
         TOPO_LAUNCH("transpose", s, transpose_kernel<<<tg2, dim3(32, 8), 0, s>>>(t2, tp_out, out, ld_out, v->nx, v->out_rows));
     } else if (do_x) {
         GaussParams p{cur, out, cur_ld, ld_out, v->nx, v->gny, cur_gy0, cur_rows, v->out_gy0, v->out_rows, w_x, lw_x};

@@ -49,7 +49,7 @@ struct VfftFwdParams {
 
 // One line (row of a T x T plane) per CTA: forward transform, output in digit-reversed order.
 template <int N, int SRC>
-__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 2) vfft_fwd_kernel(const VfftFwdParams p) {
+__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3) vfft_fwd_kernel(const VfftFwdParams p) {
     using S = FftShape<N>;
     constexpr int NT = S::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -127,7 +127,7 @@ struct VfftInvParams {
 // convolution value of window pixel (Y, n): real part = kernel a, imaginary part = kernel b; folded into the running
 // strict-'>' (max, argmax) of the output pixel it belongs to.
 template <int N, bool FOLD>
-__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 2) vfft_inv_kernel(const VfftInvParams p) {
+__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3) vfft_inv_kernel(const VfftInvParams p) {
     using S = FftShape<N>;
     constexpr int NT = S::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
