@@ -26,7 +26,7 @@ size_t fft_conv_table_bytes(int lw);
 int fft_conv_rows(const float* in, int64_t ld_in, float* out, int64_t ld_out, int n_lines, int n_glob, int in0, int in_len,
                   int out0, int out_len, const double* w, int lw, void* tables, cudaStream_t s);
 
-constexpr int kFftMinRadius = 128;  // from here the FFT pass beats 2*lw+1 float64 taps per pixel
+constexpr int kFftMinRadius = 40;  // from here the FFT pass (~1.9 ms per axis at 16384^2, any radius) beats 2*lw+1 float64 taps per pixel
 constexpr int kK = 16;  // outputs per thread along the filter axis (micro-benchmark: 41 DFMA/clk/SM vs 28 at K = 8)
 constexpr int kAxis1SmemMaxRadius = 64;  // wider axis-1 filters go through a transpose
 
