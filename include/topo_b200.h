@@ -70,7 +70,8 @@ int topo_profile_enable(int on);
 int topo_profile_dump(char* buf, size_t cap);
 /* Execution-shape switches, all on by default: "octagon" (octagon core of the shared-plane disc walk), "tiny"
  * (register sliding sums for sizes 5..13), "sx_tma" (TMA-staged Sx tile), "gauss_fft" (float64 FFT overlap-save for
- * wide Gaussian radii), "grad_fused" (single-kernel small-radius gradient).  Every setting gives the same results
+ * wide Gaussian radii), "grad_fused" (single-kernel small-radius gradient), "disc_fft" (exact disc sums of sizes >= 128
+ * by float64 FFT convolution of the integer planes instead of the prefix-plane walk).  Every setting gives the same results
  * through another kernel shape (the tests flip them to compare shapes bit for bit); nothing is read from the
  * process environment.  Returns 0, or -1 for an unknown name. */
 int topo_set_option(const char* name, int value);
@@ -146,10 +147,11 @@ int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, double 
 /* 0: this DEM / size cannot share planes (the calls then run un-cached; pass cache = NULL). */
 size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer, double zmin, double zmax);
 /* Host-only introspection (no launch): the plan topo_tpi_f32 (what = 0) / topo_std_f32 (what = 1) would run.
- * info[17]: 0 mode (0 TPI_Q, 1 TPI_X, 2 STD_I, 3 STD_F, 4 TPI_I), 1 fused, 2 hybrid, 3 tiny, 4 uses the plane
+ * info[20]: 0 mode (0 TPI_Q, 1 TPI_X, 2 STD_I, 3 STD_F, 4 TPI_I), 1 fused, 2 hybrid, 3 tiny, 4 uses the plane
  * cache, 5 octagon walk, 6 u (octagon) or a (inscribed square), 7 v, 8 corner diagonals, 9 32-bit accumulator
  * mask, 10 dynamic shared memory of the walk, 11 plane halo, 12 plane pitch, 13 plane rows, 14 workspace
- * bytes, 15 bytes of one cached plane region, 16 split square planes. */
+ * bytes, 15 bytes of one cached plane region, 16 split square planes, 17 FFT route, 18 its transform length, 19 its
+ * tiles. */
 int topo_disc_plan_info(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax,
                         int cache_max_size, int tsum_op, long long* info);
 int topo_tpi_f32(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v,

@@ -348,3 +348,45 @@ def test_sweep_graph_replay_equals_the_eager_sweep():
         assert set(sg.outputs) == set(want) and sg.launches > 50
         for key, w in want.items():
             assert torch.equal(sg.outputs[key], w), (k, key)
+
+
+def test_disc_fft_route_is_bit_identical_to_the_prefix_plane_walk():
+    """Sizes >= 128 compute their disc sums by float64 FFT convolution of the integer planes; the rounded sums are the
+    exact integers the prefix-plane walk accumulates, so TPI and STD come out bit-identical: integer and float DEMs,
+    single calls and a cached sweep with tpi + std pairs, an even size, a wide range that splits the square plane, and
+    a row band."""
+    from topo_descriptors_b200 import _lib
+
+    def run(dem, sizes, hint=None, pair=False):
+        d = DeviceDEM(dev.to_device(dem))
+        if hint:
+            d.share_disc_planes(hint)
+        out = {}
+        for s in sizes:
+            out[s] = (dev.tpi(d, s, pair_std=pair).cpu().numpy(), dev.std(d, s).cpu().numpy())
+        return out
+
+    z = fractal_dem(1300, 1500, seed=24)
+    zi = np.rint(z).astype(np.float32)
+    zw = fractal_dem(900, 1000, seed=25, zmin=0.0, zmax=8848.0, integer=True)
+    # (float DEMs: paired calls on both routes -- an unpaired float tpi walks the quantised plane, the FFT route always
+    # carries the exact T + fraction pair)
+    cases = [(zi, [129, 200, 401], None, False), (z, [161, 301], None, True), (zi, [41, 161, 401, 801], 801, True),
+             (z, [81, 241, 801], 801, True), (zw, [401], None, False)]
+    for dem, sizes, hint, pair in cases:
+        got = run(dem, sizes, hint, pair)
+        _lib.set_option("disc_fft", False)
+        try:
+            want = run(dem, sizes, hint, pair)
+        finally:
+            _lib.set_option("disc_fft", True)
+        for s in sizes:
+            assert np.array_equal(got[s][0], want[s][0]), ("tpi", s, hint, float(np.abs(got[s][0] - want[s][0]).max()))
+            assert np.array_equal(got[s][1], want[s][1]), ("std", s, hint, float(np.abs(got[s][1] - want[s][1]).max()))
+    assert maxdiff(run(zi, [401])[401][0], O.tpi_exact(zi, 401)) <= TOL_M
+    # row band in global coordinates
+    whole = DeviceDEM(dev.to_device(zi))
+    ref = dev.std(whole, 301)
+    lo, hi, halo = 500, 900, 150
+    band = DeviceDEM(whole.tensor[lo - halo : hi + halo].contiguous(), gny=1300, gy0=lo - halo, stats=whole.stats)
+    assert bool((dev.std(band, 301, lo, hi - lo) == ref[lo:hi]).all())

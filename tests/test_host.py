@@ -289,12 +289,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 801, 0, 1, 200.0, 3400.0, 0, 0) > 4 * 900 * 1440
     # with a plane cache the planes live there: the workspace shrinks and mid sizes walk the cached planes
     rng = (200.0, 3400.0)
+    # FFT route (default for sizes >= 128): the cache holds one plane spectrum per plane pair (T = 4096, one tile)
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) == 4096 * 4096 * 16
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0, *rng) == 2 * 4096 * 4096 * 16
+    assert lib.topo_disc_shares_tsum(ctypes.byref(v), 401, 1, *rng, 801) == 2  # T and the square plane ride together
+    _lib.set_option("disc_fft", False)  # the prefix-plane walk and its plane cache
     assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) > 10 * 4 * 900 * 1440
     assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0, *rng) == 2 * lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng)
     assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 41, 1, 1, *rng, 801, 0) >= 2 * 8 * 900 * 1440  # raw sums of two planes
     assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, *rng, 0) == 0
     assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 1, *rng, 801) == 1
     assert lib.topo_disc_shares_tsum(ctypes.byref(v), 41, 0, *rng, 801) == 2  # float DEM: T and fraction planes
+    _lib.set_option("disc_fft", True)
 
 
 def test_c_abi_argument_errors_are_reported_before_any_launch():
@@ -350,26 +356,29 @@ def test_disc_queries_agree_with_the_plan_over_a_size_x_range_grid():
     v = _lib.View(4096, 4096, 0, 4096, 0, 4096)
     vp = ctypes.byref(v)
     info = (ctypes.c_longlong * 32)()
-    for integer in (1, 0):
-        for zmin, zmax in ((200.0, 3400.0), (200.0, 4700.0), (0.0, 4800.0), (0.0, 8848.0), (-11000.0, 8848.0)):
-            for hint in (0, 801, 2001):
-                for size in (5, 21, 41, 201, 401, 801, 2001):
-                    if hint and size > hint:
-                        continue
-                    for what in (0, 1):
-                        assert lib.topo_disc_plan_info(vp, size, what, integer, zmin, zmax, hint, 0, info) == 0, (
-                            size, what, integer, zmin, zmax, hint, lib.topo_last_error())
-                        fused, cached, ws, off_partial = info[1], info[4], info[14], info[15]
-                        need = 0 if fused else (ws - off_partial if cached else ws)
-                        got = lib.topo_disc_workspace_bytes(vp, size, what, integer, zmin, zmax, hint, 0)
-                        assert got == need, (size, what, integer, zmin, zmax, hint, got, need)
-                    if lib.topo_disc_shares_tsum(vp, size, integer, zmin, zmax, hint):
-                        a = (ctypes.c_longlong * 32)()
-                        b = (ctypes.c_longlong * 32)()
-                        lib.topo_disc_plan_info(vp, size, 0, integer, zmin, zmax, hint, 1, a)
-                        lib.topo_disc_plan_info(vp, size, 1, integer, zmin, zmax, hint, 1, b)
-                        # TPI_I + STD_I (integer DEM) or TPI_X + STD_F (float DEM), both two-pass
-                        assert (a[0], b[0], a[1], b[1]) == ((4, 2, 0, 0) if integer else (1, 3, 0, 0))
+    for fft_on in (True, False):
+      _lib.set_option("disc_fft", fft_on)
+      for integer in (1, 0):
+          for zmin, zmax in ((200.0, 3400.0), (200.0, 4700.0), (0.0, 4800.0), (0.0, 8848.0), (-11000.0, 8848.0)):
+              for hint in (0, 801, 2001):
+                  for size in (5, 21, 41, 201, 401, 801, 2001):
+                      if hint and size > hint:
+                          continue
+                      for what in (0, 1):
+                          assert lib.topo_disc_plan_info(vp, size, what, integer, zmin, zmax, hint, 0, info) == 0, (
+                              size, what, integer, zmin, zmax, hint, lib.topo_last_error())
+                          fused, cached, ws, off_partial = info[1], info[4], info[14], info[15]
+                          need = ws if info[17] else (0 if fused else (ws - off_partial if cached else ws))
+                          got = lib.topo_disc_workspace_bytes(vp, size, what, integer, zmin, zmax, hint, 0)
+                          assert got == need, (size, what, integer, zmin, zmax, hint, got, need)
+                      if lib.topo_disc_shares_tsum(vp, size, integer, zmin, zmax, hint):
+                          a = (ctypes.c_longlong * 32)()
+                          b = (ctypes.c_longlong * 32)()
+                          lib.topo_disc_plan_info(vp, size, 0, integer, zmin, zmax, hint, 1, a)
+                          lib.topo_disc_plan_info(vp, size, 1, integer, zmin, zmax, hint, 1, b)
+                          # TPI_I + STD_I (integer DEM) or TPI_X + STD_F (float DEM), both two-pass
+                          assert (a[0], b[0], a[1], b[1]) == ((4, 2, 0, 0) if integer else (1, 3, 0, 0)) and a[17] == b[17]
+    _lib.set_option("disc_fft", False)
     # the advisor's cases: std(801) on 200..4800 and std(2001) now plan (split squares) instead of raising
     for size in (801, 2001):
         assert lib.topo_disc_plan_info(vp, size, 1, 1, 200.0, 4800.0, 0, 0, info) == 0 and info[16] == 1
@@ -377,6 +386,10 @@ def test_disc_queries_agree_with_the_plan_over_a_size_x_range_grid():
     # a cache laid out for a split square holds one more plane region
     base = lib.topo_disc_cache_bytes(vp, 801, 1, 200.0, 3400.0)
     assert base > 0 and lib.topo_disc_cache_bytes(vp, 801, 1, 0.0, 4800.0) * 2 == base * 3
+    _lib.set_option("disc_fft", True)
+    # FFT route: exactness of the rounded sums decides the split (an 0..8848 m range at size 801), not the 32-bit spans
+    assert lib.topo_disc_plan_info(vp, 801, 1, 1, 200.0, 3400.0, 0, 0, info) == 0 and (info[17], info[16]) == (1, 0)
+    assert lib.topo_disc_plan_info(vp, 801, 1, 1, 0.0, 8848.0, 0, 0, info) == 0 and (info[17], info[16]) == (1, 1)
 
 
 def test_tiler_band_plan_and_stats_merge():

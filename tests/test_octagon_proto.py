@@ -76,7 +76,23 @@ def test_cxx_planner_matches_the_prototype_for_every_odd_size():
     from topo_descriptors_b200 import _lib
 
     lib = _lib.load()
-    info = (ctypes.c_longlong * 16)()
+    info = (ctypes.c_longlong * 32)()
+    _lib.set_option("disc_fft", False)  # this test is about the prefix-plane walk (sizes >= 128 take the FFT route by default)
+    try:
+        _planner_checks(lib, info, octagon, math, ctypes, _lib)
+    finally:
+        _lib.set_option("disc_fft", True)
+    # default route for large sizes: FFT convolution of the integer planes, T = 4096 windows for a 20 km sweep
+    v = _lib.View(2048, 4096, 0, 4096, 0, 4096)
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 801, 1, 1, 0.0, 3400.0, 801, 0, info) == 0
+    assert (info[17], info[18], info[4], info[16]) == (1, 4096, 1, 0) and info[19] == 2 * 1
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 41, 1, 1, 0.0, 3400.0, 801, 0, info) == 0 and (info[17], info[4]) == (1, 1)
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 21, 1, 1, 0.0, 3400.0, 801, 0, info) == 0 and (info[17], info[4]) == (0, 0)
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 41, 1, 1, 0.0, 3400.0, 0, 0, info) == 0 and info[17] == 0
+    assert lib.topo_disc_plan_info(ctypes.byref(v), 161, 0, 0, 0.0, 3400.5, 0, 0, info) == 0 and (info[17], info[18], info[0]) == (1, 2048, 1)
+
+
+def _planner_checks(lib, info, octagon, math, ctypes, _lib):
     sizes = list(range(41, 1203, 2)) + [2001, 3001, 4095, 8191]
     for size in sizes:
         v = _lib.View(2048, 4096, 0, 4096, 0, 4096)

@@ -32,6 +32,7 @@ def needs_build():
         os.path.join(CSRC, "common.cuh"),
         os.path.join(CSRC, "tma.cuh"),
         os.path.join(CSRC, "fft_smem.cuh"),
+        os.path.join(CSRC, "fft2d.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "topo_b200.h"),
     ]
     return any(os.path.getmtime(d) > t for d in deps)

@@ -39,6 +39,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "fft2d.cuh"
 
 namespace topo {
 
@@ -94,6 +95,7 @@ struct DiscParams {
     int64_t partial_stride;
     unsigned long long* tsum;  // optional: raw sums of the T plane (trunc(z) - tmin), shared between tpi and std
     unsigned long long* fsum;  // optional, float DEMs: raw sums of the fraction plane, shared likewise
+    unsigned long long* qsum;  // optional, integer DEMs on the FFT route: raw sums of the (low half of the) square plane
     int fplane;                // index of the fraction plane among this mode's planes (-1: none)
     int nrows;   // two-pass: rows of the prefix planes
     int64_t ld_in, ld_out;
@@ -1218,12 +1220,115 @@ __global__ void __launch_bounds__(256) disc_finish_kernel(const DiscParams p) {
         unsigned long long acc[NARR];
 #pragma unroll
         for (int a = 0; a < NARR; ++a)
-            acc[a] = (a == 0 && p.tsum) ? p.tsum[idx] : (a == p.fplane && p.fsum) ? p.fsum[idx] : p.partial[a * p.partial_stride + idx];
+            acc[a] = (a == 0 && p.tsum)            ? p.tsum[idx]
+                     : (a == p.fplane && p.fsum)   ? p.fsum[idx]
+                     : (a == 1 && p.qsum)          ? p.qsum[idx]
+                                                   : p.partial[a * p.partial_stride + idx];
         if constexpr (MODE == STD_I || MODE == STD_F) {
             if (p.qsplit) acc[1] += p.partial[NARR * p.partial_stride + idx] << 16;
         }
         p.out[(int64_t)r * p.ld_out + x] = finish<MODE>(p, acc, p.out_gy0 + r, x);
     }
+}
+
+// ---- FFT route: exact disc sums of the integer planes by float64 2-D overlap-save convolution -------------------
+// The plane values are non-negative integers, so every disc sum is an integer; a float64 FFT convolution of a T x T
+// window reproduces it with an absolute error far below 1/2 (bound checked by the planner: ~1e-14 * T * max value *
+// sqrt(N)), and rounding to the nearest integer gives EXACTLY the sums the prefix-plane walk accumulates -- the same
+// float64 epilogue then yields bit-identical TPI / STD.  Cost: one inverse 2-D transform per size and plane PAIR (two
+// planes ride in the real and imaginary parts), independent of the size: 12.6 ms per pair at 16384^2 against 29-34 ms
+// per plane for the size-801 walk.  The forward transforms of the planes are shared by all sizes of a sweep (cache).
+struct DfftGeom {
+    int T, H, V, tiles_y, tiles_x;  // transform length, window halo, outputs per tile edge
+};
+
+__device__ __forceinline__ double plane_value_rt(const DiscParams& p, int mode, float z) {
+    switch (mode) {
+        case PL_T: return (double)(uint32_t)(__float2int_rz(z) - p.tmin);
+        case PL_Q: {
+            const int d = __float2int_rz(z) - p.cmid;
+            return (double)(uint32_t)(d * d);
+        }
+        case PL_QL: {
+            const int d = __float2int_rz(z) - p.cmid;
+            return (double)((uint32_t)(d * d) & 0xffffu);
+        }
+        case PL_QH: {
+            const int d = __float2int_rz(z) - p.cmid;
+            return (double)((uint32_t)(d * d) >> 16);
+        }
+        case PL_F: {
+            const float f1 = (z - (float)__float2int_rz(z)) + 1.0f;
+            return (double)(uint32_t)__float2int_rn(f1 * p.fscale);
+        }
+        default: return 0.0;
+    }
+}
+
+// first forward pass of a plane pair: window row `line` of tile `plane`; zero elevation outside the image (the
+// reference's zero padding: it converts to the planes' own "zero")
+template <int N>
+__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
+    dfft_fwd_planes_kernel(const DiscParams p, const DfftGeom g, int mode_a, int mode_b, double2* __restrict__ dst,
+                           const double2* __restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* buf = reinterpret_cast<double2*>(smem_raw);
+    const int line = blockIdx.x, plane = blockIdx.y;
+    const int ty = plane / g.tiles_x, tx = plane - ty * g.tiles_x;
+    const int gy = p.out_gy0 + ty * g.V - g.H + line, c0 = tx * g.V - g.H;
+    const bool row_ok = gy >= 0 && gy < p.gny && gy >= p.in_gy0 && gy < p.in_gy0 + p.in_rows;
+    const float* row = p.dem + (int64_t)(row_ok ? gy - p.in_gy0 : 0) * p.ld_in;
+    fft2d_forward_line<N>(buf, tw, threadIdx.x, [&](int n) -> double2 {
+        const int gx = c0 + n;
+        const float z = (row_ok && gx >= 0 && gx < p.nx) ? __ldg(row + gx) : 0.f;
+        return make_double2(plane_value_rt(p, mode_a, z), mode_b >= 0 ? plane_value_rt(p, mode_b, z) : 0.0);
+    }, dst + ((int64_t)plane * N + line) * N);
+}
+
+// first forward pass of the disc mask (circular_kernel / the square of sizes < 5), placed so that scipy's "same" crop
+// of the true convolution lands on window offset (H, H)
+template <int N>
+__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
+    dfft_fwd_disc_kernel(const DiscParams p, const DfftGeom g, double2* __restrict__ dst, const double2* __restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* buf = reinterpret_cast<double2*>(smem_raw);
+    const int line = blockIdx.x;
+    const int i = line - (g.H - p.c);  // kernel row
+    double2* out = dst + (int64_t)line * N;
+    if (i < 0 || i >= p.k) {
+        for (int n = threadIdx.x; n < N; n += FftShape<N>::NT) out[n] = make_double2(0.0, 0.0);
+        return;
+    }
+    int dxlo, dxhi;
+    kernel_row_span(p, i, dxlo, dxhi);          // DEM column offsets c - j of the row's run of ones
+    const int jlo = p.c - dxhi, jhi = p.c - dxlo;
+    fft2d_forward_line<N>(buf, tw, threadIdx.x, [&](int n) -> double2 {
+        const int j = n - (g.H - p.c);
+        return make_double2((j >= jlo && j <= jhi) ? 1.0 : 0.0, 0.0);
+    }, out);
+}
+
+// second inverse pass + rounding to the exact integer sums: window pixel (line, n) -> output pixel
+template <int N>
+__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
+    dfft_store_kernel(const DiscParams p, const DfftGeom g, const double2* __restrict__ src, const double2* __restrict__ tw,
+                      unsigned long long* __restrict__ dest_a, unsigned long long* __restrict__ dest_b, double scale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* buf = reinterpret_cast<double2*>(smem_raw);
+    const int line = blockIdx.x, plane = blockIdx.y;
+    const int ty = plane / g.tiles_x, tx = plane - ty * g.tiles_x;
+    const int oy0 = p.out_gy0 + ty * g.V;
+    const int gy = oy0 + line - 2 * g.H;
+    const int oy1 = min(oy0 + g.V, p.out_gy0 + p.out_rows);
+    if (gy < oy0 || gy >= oy1) return;  // CTA-uniform
+    const int ox0 = tx * g.V, x_lo = 2 * g.H, x_hi = x_lo + min(g.V, p.nx - ox0);
+    const double2* __restrict__ in = src + ((int64_t)plane * N + line) * N;
+    const int64_t base = (int64_t)(gy - p.out_gy0) * p.nx + ox0 - x_lo;
+    fft2d_inverse_line<N>(buf, tw, threadIdx.x, [&](int i) { return __ldg(in + i); }, [&](int n, double2 y) {
+        if (n < x_lo || n >= x_hi) return;
+        if (dest_a) dest_a[base + n] = (unsigned long long)llrint(y.x * scale);
+        if (dest_b) dest_b[base + n] = (unsigned long long)llrint(y.y * scale);
+    });
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -1240,7 +1345,32 @@ struct DiscPlan {
     size_t off_cp, off_sat, off_totq, off_totr, off_e, off_d, off_dtot, off_partial;
     int ndchunks, ndiag_threads;  // octagon tables: row chunks and diagonals of the diagonal scans
     size_t ws_bytes;
+    // FFT route
+    bool fft;
+    DfftGeom fg;
+    int fft_pairs;                  // plane pairs of this DEM class (1: integer-valued, 2: float or split squares)
+    int fft_mb0;                    // the plane that rides with T in pair 0 (the same for every call on this DEM: the
+                                    // cached spectrum of pair 0 is shared by tpi and std): F, Q, QL or none
+    size_t fft_plane_bytes;         // one spectrum: tiles x T x T x 16
+    size_t off_tw, off_dhat, off_x, off_y, off_k1, off_k2;
 };
+
+// Sizes from here take the FFT route (one inverse 2-D transform per plane pair, ~9.7 ms per pair at 16384^2 whatever the
+// size; a single call also pays the forward transforms of its planes).  Measured crossovers on B200: the cached octagon
+// walk costs 4.4 / 5.6 / 8.5 ms per PLANE at sizes 41 / 81 / 161 plus ~9 ms of table builds per plane kind and sweep.
+constexpr int kDiscFftMin = 128;        // single calls
+constexpr int kDiscFftMinCached = 33;   // inside a sweep whose plane spectra are cached
+
+static int dfft_length(int halo) {
+    if (halo <= 128) return 2048;
+    if (halo <= 640) return 4096;
+    if (halo <= 2048) return 8192;
+    return 0;
+}
+
+// |error| of a float64 FFT convolution output, with a safety factor of 4: must stay well below 1/2 for the rounding
+// to recover the exact integer sum
+static bool dfft_exact(int T, double vmax, double n) { return 4.0 * 24.0 * 1.11e-16 * (double)T * vmax * sqrt(n) < 0.25; }
 
 static long long disc_count(int k) {
     // N = number of ones of circular_kernel(k)
@@ -1399,6 +1529,44 @@ static int ilog2_floor(double x) {
 
 constexpr double kU32 = 4294967295.0;
 
+// FFT route for this size, with windows laid out for `halo` rows / columns around a tile (the size's own half, or the
+// half of the largest size of a sweep that shares the plane spectra)
+static bool fft_route(int size, int halo, bool cached = false) {
+    return option_enabled(kOptDiscFft) && size >= (cached ? kDiscFftMinCached : kDiscFftMin) && dfft_length(halo) > 0;
+}
+
+static void plan_fft_geometry(const topo_view* v, int size, int narr, int plane_halo, int pairs, DiscPlan& pl) {
+    DiscParams& p = pl.p;
+    p.nx = v->nx, p.gny = v->gny, p.in_gy0 = v->in_gy0, p.in_rows = v->in_rows;
+    p.out_gy0 = v->out_gy0, p.out_rows = v->out_rows;
+    p.k = size, p.c = (size - 1) / 2, p.mid = size / 2, p.square = size < 5;
+    p.halo = size / 2;
+    p.excl = p.c - p.mid;
+    pl.fft = true, pl.fused = false, pl.hybrid = false, pl.tiny = false, pl.cached = plane_halo > 0;
+    pl.smem = 0, pl.prefix_rows = 0;
+    DfftGeom& g = pl.fg;
+    g.H = plane_halo > 0 ? plane_halo : size / 2;
+    g.T = dfft_length(g.H);
+    g.V = g.T - 2 * g.H;
+    g.tiles_y = ceil_div(v->out_rows, g.V), g.tiles_x = ceil_div(v->nx, g.V);
+    pl.fft_pairs = pairs;
+    pl.fft_plane_bytes = (size_t)g.tiles_y * g.tiles_x * g.T * g.T * sizeof(double2);
+    auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t one = (size_t)g.T * g.T * sizeof(double2);
+    size_t off = 0;
+    pl.off_tw = off, off = align(off + (size_t)g.T * sizeof(double2));
+    pl.off_dhat = off;
+    if (!pl.cached) off = align(off + pairs * pl.fft_plane_bytes);  // with a cache the plane spectra live there
+    pl.off_x = off, off = align(off + pl.fft_plane_bytes);
+    pl.off_y = off, off = align(off + pl.fft_plane_bytes);
+    pl.off_k1 = off, off = align(off + one);
+    pl.off_k2 = off, off = align(off + one);
+    pl.off_partial = off;
+    p.partial_stride = (int64_t)p.out_rows * p.nx;
+    off += (size_t)narr * p.partial_stride * 8;
+    pl.ws_bytes = off;
+}
+
 // Fill the data-dependent constants.  what: 0 = TPI, 1 = STD.
 // span_size: the disc size the fixed-point scales are laid out for -- `size` itself, or the largest size of a sweep
 // that shares its planes through a topo_disc_cache (then every size of the sweep sees the same planes).
@@ -1414,6 +1582,10 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
     int mode, acc = 0;
     DiscParams& p = pl.p;
     memset(&p, 0, sizeof(p));
+    // shared planes / spectra: laid out for the halo of the largest size of the sweep
+    const int plane_halo = cache_size >= size ? cache_size / 2 : 0;
+    const bool fft = fft_route(size, plane_halo > 0 ? plane_halo : size / 2, plane_halo > 0);
+    pl.fft = false;
     double vmax[3] = {0, 0, 0};  // largest value a plane element can take
     double vmax_qh = 0;
     int qsplit = 0;
@@ -1426,7 +1598,9 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
         int S32 = ilog2_floor(kU32 / (n * range));
         if (S32 > 20) S32 = 20;
         if (S32 >= 13 && span_size == size) S = S32;  // (depends on the size: not for shared planes)
-        if (S >= 10 && !pair) {  // pair: tpi shares the T and fraction sums with a std of the same size (exact TPI_X)
+        // pair: tpi shares the T and fraction sums with a std of the same size (exact TPI_X); the FFT route carries two
+        // planes per transform anyway
+        if (S >= 10 && !pair && !fft) {
             mode = TPI_Q;
             p.scale = (float)ldexp(1.0, S);
             p.c0i = (int)ldexp(c0, S);
@@ -1465,13 +1639,42 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
             vmax[narr_of(mode) - 1] = ldexp(2.0, Sf);
         }
     }
+    if (fft) {
+        // the rounded FFT output must be the exact integer sum: planes whose magnitude would endanger that are split
+        // (squares) or coarsened (fraction; 2^-12 m per pixel is still far inside the tolerance)
+        const int T = dfft_length(plane_halo > 0 ? plane_halo : size / 2);
+        const double nb = (double)disc_count(span_size);
+        if ((mode == STD_I || mode == STD_F) && !qsplit && !dfft_exact(T, vmax[1], nb)) {
+            const double half = floor(trange / 2.0) + 1.0;
+            TOPO_CHECK(half <= 65535.0, "DEM range %.0f too wide for the integer squares of std", trange);
+            qsplit = 1;
+            vmax[1] = 65535.0;
+            vmax_qh = floor(half * half / 65536.0);
+        }
+        const double half_q = floor(trange / 2.0) + 1.0;
+        if (mode == TPI_I) {
+            // the square plane rides along with T (and is kept for a following std): split it exactly when std would
+            if (!(span * half_q * half_q < kU32) || !dfft_exact(T, half_q * half_q, nb)) qsplit = half_q <= 65535.0 ? 1 : 0;
+        }
+        pl.fft_mb0 = !all_integer ? PL_F : (half_q > 65535.0 ? -1 : (qsplit ? PL_QL : PL_Q));
+        if (mode == TPI_X || mode == STD_F) {
+            int Sf = ilog2_floor((double)p.fscale);
+            while (Sf > 12 && !dfft_exact(T, ldexp(2.0, Sf), nb)) --Sf;
+            p.fscale = (float)ldexp(1.0, Sf);
+            p.inv_fscale = ldexp(1.0, -Sf);
+        }
+    }
     for (int a = 0; a < narr_of(mode); ++a)
         if (n * vmax[a] < kU32) acc |= 1 << a;
     pl.mode = mode;
-    // shared planes: laid out for the halo of the largest size of the sweep
-    const int plane_halo = cache_size >= size ? cache_size / 2 : 0;
     pl.cached = plane_halo > 0;
-    if (plan_geometry(v, size, narr_of(mode) + qsplit, max_rb(mode), pl, plane_halo, qsplit != 0)) return -1;
+    if (fft) {
+        // plane pairs: (T, Q | QL | F) and, for float DEMs or split squares, (Q | QL | QH, QH | -)
+        const int pairs = (all_integer ? 1 : 2) + ((all_integer && qsplit) ? 1 : 0);
+        plan_fft_geometry(v, size, narr_of(mode) + ((mode == STD_I || mode == STD_F) ? qsplit : 0), plane_halo, pairs, pl);
+    } else {
+        if (plan_geometry(v, size, narr_of(mode) + qsplit, max_rb(mode), pl, plane_halo, qsplit != 0)) return -1;
+    }
     if (pl.fused) pl.cached = false;
     p.qsplit = qsplit;
     p.fplane = mode == TPI_X ? 1 : mode == STD_F ? 2 : -1;
@@ -1504,7 +1707,11 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
 static int plan_disc(const topo_view* v, int size, int what, int all_integer, double zmin, double zmax, DiscPlan& pl,
                      int cache_size = 0, bool pair = false) {
     if (cache_size >= size && size >= 2) {
-        if (plan_disc_impl(v, size, what, all_integer, zmin, zmax, pl, cache_size, cache_size, pair) == 0 && !pl.fused) return 0;
+        // a sweep whose largest size takes the FFT route keeps plane SPECTRA in its cache: only FFT sizes can use it
+        const bool cache_is_fft = fft_route(cache_size, cache_size / 2);
+        if (!cache_is_fft || size >= kDiscFftMinCached) {
+            if (plan_disc_impl(v, size, what, all_integer, zmin, zmax, pl, cache_size, cache_size, pair) == 0 && !pl.fused) return 0;
+        }
     }
     return plan_disc_impl(v, size, what, all_integer, zmin, zmax, pl, 0, size, pair);
 }
@@ -1701,6 +1908,102 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo
     }
 }
 
+// ---- FFT route: launches ------------------------------------------------------------------------------------------
+template <int N>
+static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo_disc_cache* cache, unsigned char* ws) {
+    using S = FftShape<N>;
+    const DiscParams& p = pl.p;
+    const DfftGeom& g = pl.fg;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    TOPO_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_planes_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_disc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute(dfft_store_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        if (fft2d_set_smem_attributes<N>()) return -2;
+        if (dev < 64) attr_set[dev] = true;
+    }
+    double2* tw = reinterpret_cast<double2*>(ws + pl.off_tw);
+    double2* X = reinterpret_cast<double2*>(ws + pl.off_x);
+    double2* Y = reinterpret_cast<double2*>(ws + pl.off_y);
+    double2* K1 = reinterpret_cast<double2*>(ws + pl.off_k1);
+    double2* K2 = reinterpret_cast<double2*>(ws + pl.off_k2);
+    const int planes = g.tiles_y * g.tiles_x;
+    TOPO_CHECK(planes <= 65535, "too many tiles for one launch: split the DEM in row bands");
+    const dim3 tgrid(N / 32, N / 32, planes), kgrid(N / 32, N / 32, 1);
+    const bool reuse = tsum_op == 2;  // a previous call of the pair left the sums of plane pair 0 in tsum / qsum / fsum
+    const int q_lo = p.qsplit ? PL_QL : PL_Q;
+    unsigned long long* part = p.partial;
+    const int64_t ps = p.partial_stride;
+
+    // the plane pairs this descriptor needs: {mode a, mode b, destination a, destination b}
+    struct Job { int pair, ma, mb; unsigned long long *da, *db; };
+    Job jobs[2];
+    int njobs = 0;
+    switch (pl.mode) {
+        case TPI_I:
+            if (!reuse) jobs[njobs++] = {0, PL_T, pl.fft_mb0, p.tsum ? p.tsum : part, pl.fft_mb0 >= 0 ? p.qsum : nullptr};
+            break;
+        case TPI_X:
+            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum ? p.tsum : part, p.fsum ? p.fsum : part + ps};
+            break;
+        case STD_I:
+            if (!reuse) jobs[njobs++] = {0, PL_T, q_lo, p.tsum ? p.tsum : part, p.qsum ? p.qsum : part + ps};
+            if (p.qsplit) jobs[njobs++] = {1, PL_QH, -1, part + 2 * ps, nullptr};
+            break;
+        default:  // STD_F
+            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum ? p.tsum : part, p.fsum ? p.fsum : part + 2 * ps};
+            jobs[njobs++] = {1, q_lo, p.qsplit ? PL_QH : -1, part + ps, p.qsplit ? part + 3 * ps : nullptr};
+            break;
+    }
+    if (njobs > 0) {
+        TOPO_LAUNCH("disc_fft_twiddles", s, fft_twiddle_kernel<<<ceil_div(N, 256), 256, 0, s>>>(tw, N));
+        // spectrum of the disc mask
+        TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(p, g, K1, tw)));
+        TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
+        TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
+    }
+    const double scale = 1.0 / ((double)N * (double)N);
+    for (int j = 0; j < njobs; ++j) {
+        const Job& job = jobs[j];
+        double2* dhat;
+        bool have = false;
+        if (cache) {
+            TOPO_CHECK(cache->bytes >= (size_t)pl.fft_pairs * pl.fft_plane_bytes, "plane cache too small: need %zu bytes, got %zu",
+                       (size_t)pl.fft_pairs * pl.fft_plane_bytes, cache->bytes);
+            dhat = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(cache->mem) + (size_t)job.pair * pl.fft_plane_bytes);
+            have = (cache->valid >> (16 + job.pair)) & 1;
+        } else {
+            dhat = reinterpret_cast<double2*>(ws + pl.off_dhat + (size_t)job.pair * pl.fft_plane_bytes);
+        }
+        if (!have) {
+            TOPO_LAUNCH("disc_fft_planes", s, (dfft_fwd_planes_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(p, g, job.ma, job.mb, X, tw)));
+            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+            TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(Y, dhat, tw)));
+            if (cache) cache->valid |= 1 << (16 + job.pair);
+        }
+        TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, X, tw)));
+        TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+        TOPO_LAUNCH("disc_fft_store", s, (dfft_store_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, scale)));
+    }
+    switch (pl.mode) {
+        case TPI_I: TOPO_LAUNCH("disc_finish<TPI_I>", s, disc_finish_kernel<TPI_I><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
+        case TPI_X: TOPO_LAUNCH("disc_finish<TPI_X>", s, disc_finish_kernel<TPI_X><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
+        case STD_I: TOPO_LAUNCH("disc_finish<STD_I>", s, disc_finish_kernel<STD_I><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
+        default: TOPO_LAUNCH("disc_finish<STD_F>", s, disc_finish_kernel<STD_F><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
+    }
+    return 0;
+}
+
+static int launch_fft_route(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo_disc_cache* cache, unsigned char* ws) {
+    switch (pl.fg.T) {
+        case 2048: return launch_fft_route_n<2048>(pl, tsum_op, s, cache, ws);
+        case 4096: return launch_fft_route_n<4096>(pl, tsum_op, s, cache, ws);
+        default: return launch_fft_route_n<8192>(pl, tsum_op, s, cache, ws);
+    }
+}
+
 static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out, const topo_view* v, int size,
                     int what, int all_integer, double zmin, double zmax, unsigned long long* tsum, int tsum_op,
                     topo_disc_cache* cache, void* ws, size_t ws_bytes, void* stream) {
@@ -1719,6 +2022,23 @@ static int run_disc(const float* dem, int64_t ld_in, float* out, int64_t ld_out,
     if (check_band(v, pl.p.halo)) return -1;
     pl.p.dem = dem, pl.p.out = out, pl.p.ld_in = ld_in, pl.p.ld_out = ld_out;
     cudaStream_t s = (cudaStream_t)stream;
+    if (pl.fft) {
+        TOPO_CHECK(ws != nullptr && ws_bytes >= pl.ws_bytes, "workspace too small: need %zu bytes, got %zu", pl.ws_bytes, ws_bytes);
+        TOPO_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+        if (cache) TOPO_CHECK((reinterpret_cast<uintptr_t>(cache->mem) & 255) == 0, "plane cache must be 256-byte aligned");
+        pl.p.partial = reinterpret_cast<unsigned long long*>((unsigned char*)ws + pl.off_partial);
+        if (tsum_op != 0) {
+            TOPO_CHECK(tsum != nullptr, "tsum_op %d needs a plane-sum buffer", tsum_op);
+            pl.p.tsum = tsum;
+            // the second shared plane sits right behind the first (topo_disc_shares_tsum == 2): the fraction plane of
+            // float DEMs, the (low half of the) square plane of integer-valued ones
+            if (!all_integer)
+                pl.p.fsum = tsum + (int64_t)v->out_rows * v->nx;
+            else
+                pl.p.qsum = tsum + (int64_t)v->out_rows * v->nx;
+        }
+        return launch_fft_route(pl, tsum_op, s, cache, reinterpret_cast<unsigned char*>(ws));
+    }
     if (!pl.fused) {
         // with a plane cache the workspace only holds the raw sums of the multi-plane modes
         const size_t ws_need = cache ? pl.ws_bytes - pl.off_partial : pl.ws_bytes;
@@ -1784,6 +2104,7 @@ size_t topo_disc_workspace_bytes(const topo_view* v, int size, int what, int all
                                  int cache_max_size, int tsum_op) {
     DiscPlan pl;
     if (!quiet_plan(v, size, what, all_integer, zmin, zmax, cache_max_size, pl, tsum_op != 0)) return 0;
+    if (pl.fft) return pl.ws_bytes;  // (already without the plane spectra when they live in the cache)
     if (pl.fused) return 0;
     // with a plane cache the planes live there and the workspace only holds the raw plane sums
     return pl.cached ? pl.ws_bytes - pl.off_partial : pl.ws_bytes;
@@ -1796,8 +2117,8 @@ int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, double 
     DiscPlan a, b;
     if (!quiet_plan(v, size, 0, all_integer, zmin, zmax, cache_max_size, a, true)) return 0;
     if (!quiet_plan(v, size, 1, all_integer, zmin, zmax, cache_max_size, b, true)) return 0;
-    if (a.fused || b.fused || a.p.tmin != b.p.tmin) return 0;
-    if (a.mode == TPI_I && b.mode == STD_I) return 1;
+    if (a.fused || b.fused || a.p.tmin != b.p.tmin || a.fft != b.fft) return 0;
+    if (a.mode == TPI_I && b.mode == STD_I) return a.fft ? 2 : 1;  // FFT route: the square plane rides along with T
     if (a.mode == TPI_X && b.mode == STD_F && a.p.fscale == b.p.fscale) return 2;
     return 0;
 }
@@ -1805,6 +2126,7 @@ int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, double 
 size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer, double zmin, double zmax) {
     DiscPlan pl;
     if (!quiet_plan(v, max_size, 1, all_integer, zmin, zmax, max_size, pl)) return 0;
+    if (pl.fft) return pl.cached ? (size_t)pl.fft_pairs * pl.fft_plane_bytes : 0;  // plane spectra, one per pair
     if (pl.fused || !pl.cached) return 0;
     // integer-valued DEMs use two plane kinds (trunc(z) - tmin, its square); float DEMs add the fraction and the
     // quantised-elevation planes; a split square adds its high half
@@ -1823,6 +2145,7 @@ int topo_disc_plan_info(const topo_view* v, int size, int what, int all_integer,
     info[5] = pl.p.oct, info[6] = pl.p.asq, info[7] = pl.p.oct_v, info[8] = pl.p.oct_ndiag, info[9] = pl.acc;
     info[10] = (long long)pl.smem, info[11] = pl.p.halo, info[12] = pl.p.pitch, info[13] = pl.prefix_rows;
     info[14] = (long long)pl.ws_bytes, info[15] = (long long)pl.off_partial, info[16] = pl.p.qsplit;
+    info[17] = pl.fft, info[18] = pl.fft ? pl.fg.T : 0, info[19] = pl.fft ? pl.fg.tiles_y * pl.fg.tiles_x : 0;
     return 0;
 }
 

@@ -16,7 +16,7 @@
 //             pass, transpose, second inverse pass fused with the fold into the running maximum.
 #include <math.h>
 
-#include "fft_smem.cuh"
+#include "fft2d.cuh"
 
 namespace topo {
 
@@ -35,14 +35,13 @@ struct VfftKernelPair {
     float angle_a, angle_b;
 };
 
-enum { VSRC_DEM = 0, VSRC_KERN = 1, VSRC_CPLX = 2 };
+enum { VSRC_DEM = 0, VSRC_KERN = 1 };
 
 struct VfftFwdParams {
     VfftGeom g;
     const float* dem;
     int64_t ld_in;
     VfftKernelPair kp;
-    const double2* src;  // VSRC_CPLX: [planes][T][T] natural order
     double2* dst;        // [planes][T][T], digit-reversed along the line
     const double2* tw;
 };
@@ -77,11 +76,11 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3) vfft_fwd_k
         return;
     }
     const double2* __restrict__ tw = p.tw;
-    fft_forward_outer<N>(buf, tw, tid, [&](int n) -> double2 {
+    fft2d_forward_line<N>(buf, tw, tid, [&](int n) -> double2 {
         if constexpr (SRC == VSRC_DEM) {
             const int gx = c0 + n;
             return make_double2((gx >= 0 && gx < g.nx) ? (double)__ldg(row + gx) : 0.0, 0.0);
-        } else if constexpr (SRC == VSRC_KERN) {
+        } else {
             // kernel element (i, j) sits at window (i + HB - cy, j + WB - cx): one crop offset for every kernel
             double re = 0.0, im = 0.0;
             const int ia = line - (g.HB - (p.kp.ha - 1) / 2), ja = n - (g.WB - (p.kp.wa - 1) / 2);
@@ -91,21 +90,8 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3) vfft_fwd_k
                 if (ib >= 0 && ib < p.kp.hb && jb >= 0 && jb < p.kp.wb) im = (double)__ldg(p.kp.kb + (int64_t)ib * p.kp.wb + jb);
             }
             return make_double2(re, im);
-        } else {
-            return __ldg(p.src + ((int64_t)plane * N + line) * N + n);
         }
-    });
-    // innermost (stride-1) stage in place, then a coalesced copy-out
-    for (int u = tid; u < N / 8; u += NT) {
-        double2 v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = buf[pad(8 * u + q)];
-        dft8<false>(v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) buf[pad(8 * u + q)] = v[q];
-    }
-    __syncthreads();
-    for (int i = tid; i < N; i += NT) out[i] = buf[pad(i)];
+    }, out);
 }
 
 struct VfftInvParams {
@@ -122,75 +108,38 @@ struct VfftInvParams {
     double scale;       // 1 / T^2
 };
 
-// One line per CTA: inverse transform of a digit-reversed line.  FOLD = false: the line is D^ * K^ (first inverse pass,
-// along the window rows' frequency axis), result stored.  FOLD = true: second inverse pass; sample n of line Y is the
-// convolution value of window pixel (Y, n): real part = kernel a, imaginary part = kernel b; folded into the running
-// strict-'>' (max, argmax) of the output pixel it belongs to.
-template <int N, bool FOLD>
-__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3) vfft_inv_kernel(const VfftInvParams p) {
-    using S = FftShape<N>;
-    constexpr int NT = S::NT;
+// Second inverse pass, one line per CTA: sample n of line Y is the convolution value of window pixel (Y, n): real part =
+// kernel a, imaginary part = kernel b; folded into the running strict-'>' (max, argmax) of the output pixel it belongs to.
+template <int N>
+__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3) vfft_fold_kernel(const VfftInvParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
     const int tid = threadIdx.x;
     const int line = blockIdx.x, plane = blockIdx.y;
     const VfftGeom& g = p.g;
     const double2* __restrict__ src = p.a + ((int64_t)plane * N + line) * N;
-    int gy = 0, ox0 = 0, x_lo = 0, x_hi = 0;
-    if constexpr (FOLD) {
-        // window row `line` <-> output row gy = tile's first output row + line - (HT + HB)
-        const int ty = plane / g.tiles_x, tx = plane - ty * g.tiles_x;
-        const int oy0 = g.out_gy0 + ty * g.V_y;
-        gy = oy0 + line - (g.HT + g.HB);
-        const int oy1 = min(oy0 + g.V_y, g.out_gy0 + g.out_rows);
-        if (gy < oy0 || gy >= oy1) return;  // halo rows of the window: nothing to fold (CTA-uniform)
-        ox0 = tx * g.V_x;
-        x_lo = g.WT + g.WB;                                    // window column of output column ox0
-        x_hi = x_lo + min(g.V_x, g.nx - ox0);
-        for (int i = tid; i < N; i += NT) buf[pad(i)] = __ldg(src + i);
-    } else {
-        const double2* __restrict__ kk = p.k + (int64_t)line * N;
-        for (int i = tid; i < N; i += NT) buf[pad(i)] = cmul(__ldg(src + i), __ldg(kk + i));
-    }
-    __syncthreads();
-    for (int u = tid; u < N / 8; u += NT) {
-        double2 v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = buf[pad(8 * u + q)];
-        dft8<true>(v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) buf[pad(8 * u + q)] = v[q];
-    }
-    __syncthreads();
-    const double2* __restrict__ tw = p.tw;
-    if constexpr (FOLD) {
-        float* nrow = p.norm + (int64_t)(gy - g.out_gy0) * p.ld_out + ox0 - x_lo;
-        float* drow = p.dir + (int64_t)(gy - g.out_gy0) * p.ld_out + ox0 - x_lo;
-        fft_inverse_outer<N>(buf, tw, tid, [&](int n, double2 y) {
-            if (n < x_lo || n >= x_hi) return;
-            float best = nrow[n], bdir = drow[n];
-            const float va = (float)(y.x * p.scale);
-            if (va > best) best = va, bdir = p.angle_a;
-            if (p.has_b) {
-                const float vb = (float)(y.y * p.scale);
-                if (vb > best) best = vb, bdir = p.angle_b;
-            }
-            nrow[n] = best, drow[n] = bdir;
-        });
-    } else {
-        double2* out = p.dst + ((int64_t)plane * N + line) * N;
-        fft_inverse_outer<N>(buf, tw, tid, [&](int n, double2 y) { out[n] = y; });
-    }
-}
-
-// [planes][n][n] complex transpose, 32 x 32 tiles
-__global__ void __launch_bounds__(256) vfft_transpose_kernel(const double2* __restrict__ in, double2* __restrict__ out, int n) {
-    __shared__ double2 t[32][33];
-    const int64_t base = (int64_t)blockIdx.z * n * n;
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) t[i][threadIdx.x] = __ldg(in + base + (int64_t)(r0 + i) * n + c0 + threadIdx.x);
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) out[base + (int64_t)(c0 + i) * n + r0 + threadIdx.x] = t[threadIdx.x][i];
+    // window row `line` <-> output row gy = tile's first output row + line - (HT + HB)
+    const int ty = plane / g.tiles_x, tx = plane - ty * g.tiles_x;
+    const int oy0 = g.out_gy0 + ty * g.V_y;
+    const int gy = oy0 + line - (g.HT + g.HB);
+    const int oy1 = min(oy0 + g.V_y, g.out_gy0 + g.out_rows);
+    if (gy < oy0 || gy >= oy1) return;  // halo rows of the window: nothing to fold (CTA-uniform)
+    const int ox0 = tx * g.V_x;
+    const int x_lo = g.WT + g.WB;  // window column of output column ox0
+    const int x_hi = x_lo + min(g.V_x, g.nx - ox0);
+    float* nrow = p.norm + (int64_t)(gy - g.out_gy0) * p.ld_out + ox0 - x_lo;
+    float* drow = p.dir + (int64_t)(gy - g.out_gy0) * p.ld_out + ox0 - x_lo;
+    fft2d_inverse_line<N>(buf, p.tw, tid, [&](int i) { return __ldg(src + i); }, [&](int n, double2 y) {
+        if (n < x_lo || n >= x_hi) return;
+        float best = nrow[n], bdir = drow[n];
+        const float va = (float)(y.x * p.scale);
+        if (va > best) best = va, bdir = p.angle_a;
+        if (p.has_b) {
+            const float vb = (float)(y.y * p.scale);
+            if (vb > best) best = vb, bdir = p.angle_b;
+        }
+        nrow[n] = best, drow[n] = bdir;
+    });
 }
 
 __global__ void vfft_init_kernel(float* __restrict__ norm, float* __restrict__ dir, int64_t ld, int rows, int nx, int finish) {
@@ -259,9 +208,8 @@ static int vfft_run(const VfftGeom& g, const float* dem, int64_t ld_in, float* n
     if (dev >= 64 || !attr_set[dev]) {
         TOPO_CUDA(cudaFuncSetAttribute(vfft_fwd_kernel<N, VSRC_DEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
         TOPO_CUDA(cudaFuncSetAttribute(vfft_fwd_kernel<N, VSRC_KERN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute(vfft_fwd_kernel<N, VSRC_CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute(vfft_inv_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute(vfft_inv_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute(vfft_fold_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        if (fft2d_set_smem_attributes<N>()) return -2;
         if (dev < 64) attr_set[dev] = true;
     }
     const VfftWs L = vfft_ws_layout(g);
@@ -282,9 +230,8 @@ static int vfft_run(const VfftGeom& g, const float* dem, int64_t ld_in, float* n
     const dim3 tgrid(N / 32, N / 32, planes), kgrid(N / 32, N / 32, 1);
     f.dst = X;
     TOPO_LAUNCH("valley_fft_fwd", s, (vfft_fwd_kernel<N, VSRC_DEM><<<dim3(N, planes), S::NT, S::SMEM, s>>>(f)));
-    TOPO_LAUNCH("valley_fft_transpose", s, vfft_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
-    f.src = Y, f.dst = dhat;
-    TOPO_LAUNCH("valley_fft_fwd", s, (vfft_fwd_kernel<N, VSRC_CPLX><<<dim3(N, planes), S::NT, S::SMEM, s>>>(f)));
+    TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+    TOPO_LAUNCH("valley_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(Y, dhat, tw)));
 
     VfftInvParams q{};
     q.g = g, q.tw = tw, q.norm = norm, q.dir = dir, q.ld_out = ld_out, q.scale = 1.0 / ((double)N * (double)N);
@@ -298,15 +245,13 @@ static int vfft_run(const VfftGeom& g, const float* dem, int64_t ld_in, float* n
         // K^ of the pair
         f.kp = kp, f.dst = K1;
         TOPO_LAUNCH("valley_fft_fwd", s, (vfft_fwd_kernel<N, VSRC_KERN><<<dim3(N, 1), S::NT, S::SMEM, s>>>(f)));
-        TOPO_LAUNCH("valley_fft_transpose", s, vfft_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
-        f.src = K2, f.dst = K1;
-        TOPO_LAUNCH("valley_fft_fwd", s, (vfft_fwd_kernel<N, VSRC_CPLX><<<dim3(N, 1), S::NT, S::SMEM, s>>>(f)));
+        TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
+        TOPO_LAUNCH("valley_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
         // all tiles: D^ * K^ -> inverse along the rows' axis -> transpose -> inverse + fold
-        q.a = dhat, q.k = K1, q.dst = X;
-        TOPO_LAUNCH("valley_fft_inv", s, (vfft_inv_kernel<N, false><<<dim3(N, planes), S::NT, S::SMEM, s>>>(q)));
-        TOPO_LAUNCH("valley_fft_transpose", s, vfft_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+        TOPO_LAUNCH("valley_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, X, tw)));
+        TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
         q.a = Y, q.angle_a = kp.angle_a, q.angle_b = kp.angle_b, q.has_b = kp.kb != nullptr;
-        TOPO_LAUNCH("valley_fft_fold", s, (vfft_inv_kernel<N, true><<<dim3(N, planes), S::NT, S::SMEM, s>>>(q)));
+        TOPO_LAUNCH("valley_fft_fold", s, (vfft_fold_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(q)));
     }
     TOPO_LAUNCH("valley_fft_init", s, vfft_init_kernel<<<kNumSMs * 8, 256, 0, s>>>(norm, dir, ld_out, g.out_rows, g.nx, 1));
     return 0;
