@@ -51,8 +51,13 @@ if __name__ == "__main__":
     nx, ny = len(x), len(y)
     domain = {"x": slice(x[nx // 10], x[-nx // 10]), "y": slice(y[ny // 10], y[-ny // 10])}
 
-    # define the convolution scales in meters
-    scales_meters = [100, 300, 500, 1000, 2000, 4000, 6000, 10000, 20000]
+    # define the convolution scales in meters (the reference's own list, 100 m ... 100 km)
+    scales_meters = [100, 300, 500, 1000, 2000, 4000, 6000, 10000, 20000, 30000, 60000, 100000]
+    # valley / ridge: the rotated kernel of a scale must fit the largest FFT window (4096 px)
+    res = abs(float(x[1] - x[0]))
+    vr_scales = [sc for sc in scales_meters[3:] if sc / res * 1.4143 <= 4096]
+    if len(vr_scales) < len(scales_meters[3:]):
+        logger.info(f"valley/ridge: scales {scales_meters[3 + len(vr_scales):]} m exceed the 4096 px kernel extent of the FFT route, skipped")
 
     # smoothed DEM
     tp.compute_dem(dem_ds, scales_meters, ind_nans=ind_nans, crop=domain, outdir=args.outdir)
@@ -64,9 +69,9 @@ if __name__ == "__main__":
     # standard deviation of surface
     tp.compute_std(dem_ds, scales_meters, ind_nans=ind_nans, crop=domain, outdir=args.outdir)
     # valley / ridge index with prior smoothing
-    tp.compute_valley_ridge(dem_ds, scales_meters[3:5], mode="valley", flat_list=[0, 0.2, 0.4], smth_factors=0.5,
+    tp.compute_valley_ridge(dem_ds, vr_scales, mode="valley", flat_list=[0, 0.2, 0.4], smth_factors=0.5,
                             ind_nans=ind_nans, crop=domain, outdir=args.outdir)
-    tp.compute_valley_ridge(dem_ds, scales_meters[3:5], mode="ridge", flat_list=[0, 0.15, 0.3], smth_factors=0.5,
+    tp.compute_valley_ridge(dem_ds, vr_scales, mode="ridge", flat_list=[0, 0.15, 0.3], smth_factors=0.5,
                             ind_nans=ind_nans, crop=domain, outdir=args.outdir)
     # Sx for one azimuth
     tp.compute_sx(dem_ds, 0, 1000, crop=domain, outdir=args.outdir)

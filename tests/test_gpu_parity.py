@@ -179,27 +179,38 @@ def test_tpi_std_share_disc_sums():
 
 
 def test_disc_plane_cache_is_transparent():
-    """A multi-scale sweep shares the size-independent prefix planes: identical to the unshared calls, in any
-    order of sizes, for odd (hybrid), even and fused sizes, whole images and row bands."""
+    """A multi-scale sweep shares size-independent data -- the plane spectra of the FFT route, or the prefix planes and
+    octagon tables of the walk (disc_fft off): identical to the unshared calls, in any order of sizes, for odd, even
+    and fused sizes, whole images and row bands."""
+    from topo_descriptors_b200 import _lib
+
     zi = fractal_dem(450, 520, seed=15, integer=True)
     plain = DeviceDEM(dev.to_device(zi))
     sizes = [151, 7, 201, 120, 301, 33]
-    want = {s: (dev.tpi(plain, s, share=False), dev.std(plain, s, share=False)) for s in sizes}
+    _lib.set_option("disc_fft", False)
+    try:
+        want = {s: (dev.tpi(plain, s, share=False), dev.std(plain, s, share=False)) for s in sizes}
+        shared = DeviceDEM(dev.to_device(zi)).share_disc_planes(max(sizes))
+        for s in sizes:
+            assert bool((dev.tpi(shared, s) == want[s][0]).all()) and bool((dev.std(shared, s) == want[s][1]).all()), s
+        assert shared._plane_cache is not None and shared._plane_cache[1].valid == 15
+        shared.release_disc_planes()
+        # the cached walk uses the octagon decomposition (diagonal tables); the square + caps walk must agree bit for bit
+        _lib.set_option("octagon", False)
+        try:
+            square = DeviceDEM(dev.to_device(zi)).share_disc_planes(max(sizes))
+            for s in (301, 151, 201):
+                assert bool((dev.tpi(square, s) == want[s][0]).all()) and bool((dev.std(square, s) == want[s][1]).all()), s
+        finally:
+            _lib.set_option("octagon", True)
+    finally:
+        _lib.set_option("disc_fft", True)
+    # default: the sweep caches the spectrum of the (T, Q) plane pair; every size from 33 up reuses it
     shared = DeviceDEM(dev.to_device(zi)).share_disc_planes(max(sizes))
     for s in sizes:
         assert bool((dev.tpi(shared, s) == want[s][0]).all()) and bool((dev.std(shared, s) == want[s][1]).all()), s
-    assert shared._plane_cache is not None and shared._plane_cache[1].valid == 15
+    assert shared._plane_cache is not None and shared._plane_cache[1].valid == 1 << 16
     shared.release_disc_planes()
-    # the cached walk uses the octagon decomposition (diagonal tables); the square + caps walk must agree bit for bit
-    from topo_descriptors_b200 import _lib
-
-    _lib.set_option("octagon", False)
-    try:
-        square = DeviceDEM(dev.to_device(zi)).share_disc_planes(max(sizes))
-        for s in (301, 151, 201):
-            assert bool((dev.tpi(square, s) == want[s][0]).all()) and bool((dev.std(square, s) == want[s][1]).all()), s
-    finally:
-        _lib.set_option("octagon", True)
     # a row band with enough halo for the largest size
     lo, hi, halo = 120, 300, max(sizes) // 2
     band = _band(plain.tensor, lo, hi, halo, plain.stats).share_disc_planes(max(sizes))
