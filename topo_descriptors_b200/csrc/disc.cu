@@ -1308,11 +1308,15 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     }, out);
 }
 
-// second inverse pass + rounding to the exact integer sums: window pixel (line, n) -> output pixel
-template <int N>
+// second inverse pass + rounding to the exact integer sums: window pixel (line, n) -> output pixel.
+// FIN < 0: store the raw sums of the pair.  FIN = descriptor mode: this is the LAST pair of the descriptor -- gather the
+// other planes' sums (left by an earlier pair of this call or by the tpi of a tpi + std pair) and finish in place, which
+// saves the 16 B/px round trip of the raw sums and the separate finish pass.
+template <int N, int FIN>
 __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     dfft_store_kernel(const DiscParams p, const DfftGeom g, const double2* __restrict__ src, const double2* __restrict__ tw,
-                      unsigned long long* __restrict__ dest_a, unsigned long long* __restrict__ dest_b, double scale) {
+                      unsigned long long* __restrict__ dest_a, unsigned long long* __restrict__ dest_b, int mode_a, int mode_b,
+                      double scale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
     const int line = blockIdx.x, plane = blockIdx.y;
@@ -1324,10 +1328,35 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     const int ox0 = tx * g.V, x_lo = 2 * g.H, x_hi = x_lo + min(g.V, p.nx - ox0);
     const double2* __restrict__ in = src + ((int64_t)plane * N + line) * N;
     const int64_t base = (int64_t)(gy - p.out_gy0) * p.nx + ox0 - x_lo;
+    float* orow = p.out + (int64_t)(gy - p.out_gy0) * p.ld_out + ox0 - x_lo;
     fft2d_inverse_line<N>(buf, tw, threadIdx.x, [&](int i) { return __ldg(in + i); }, [&](int n, double2 y) {
         if (n < x_lo || n >= x_hi) return;
-        if (dest_a) dest_a[base + n] = (unsigned long long)llrint(y.x * scale);
-        if (dest_b) dest_b[base + n] = (unsigned long long)llrint(y.y * scale);
+        const unsigned long long va = (unsigned long long)llrint(y.x * scale), vb = (unsigned long long)llrint(y.y * scale);
+        const int64_t idx = base + n;
+        if (dest_a) dest_a[idx] = va;
+        if (dest_b) dest_b[idx] = vb;
+        if constexpr (FIN >= 0) {
+            constexpr int NARR = ModeTraits<FIN>::NARR;
+            unsigned long long acc[NARR];
+#pragma unroll
+            for (int a = 0; a < NARR; ++a) {
+                const int pm = a == 0 ? PL_T : (a == p.fplane ? PL_F : (p.qsplit ? PL_QL : PL_Q));  // the plane of slot a
+                if (pm == mode_a)
+                    acc[a] = va;
+                else if (pm == mode_b)
+                    acc[a] = vb;
+                else
+                    acc[a] = (a == 0 && p.tsum)          ? p.tsum[idx]
+                             : (a == p.fplane && p.fsum) ? p.fsum[idx]
+                             : (a == 1 && p.qsum)        ? p.qsum[idx]
+                                                         : p.partial[a * p.partial_stride + idx];
+            }
+            if constexpr (FIN == STD_I || FIN == STD_F) {
+                if (p.qsplit)  // the high half of a split square plane: this pair's, or left by an earlier one
+                    acc[1] += (mode_a == PL_QH ? va : mode_b == PL_QH ? vb : p.partial[NARR * p.partial_stride + idx]) << 16;
+            }
+            orow[n] = finish<FIN>(p, acc, gy, ox0 - x_lo + n);
+        }
     });
 }
 
@@ -1920,7 +1949,11 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
     if (dev >= 64 || !attr_set[dev]) {
         TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_planes_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
         TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_disc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute(dfft_store_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, -1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, TPI_I>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, TPI_X>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_I>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_F>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
         if (fft2d_set_smem_attributes<N>()) return -2;
         if (dev < 64) attr_set[dev] = true;
     }
@@ -1942,19 +1975,26 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
     Job jobs[2];
     int njobs = 0;
     switch (pl.mode) {
+        // (the LAST job finishes the descriptor in its store pass and only keeps raw sums a later call will reuse;
+        // earlier jobs leave their sums in tsum / qsum / fsum or the workspace)
         case TPI_I:
-            if (!reuse) jobs[njobs++] = {0, PL_T, pl.fft_mb0, p.tsum ? p.tsum : part, pl.fft_mb0 >= 0 ? p.qsum : nullptr};
+            if (!reuse) jobs[njobs++] = {0, PL_T, pl.fft_mb0, p.tsum, pl.fft_mb0 >= 0 ? p.qsum : nullptr};
             break;
         case TPI_X:
-            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum ? p.tsum : part, p.fsum ? p.fsum : part + ps};
+            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum, p.fsum};
             break;
         case STD_I:
-            if (!reuse) jobs[njobs++] = {0, PL_T, q_lo, p.tsum ? p.tsum : part, p.qsum ? p.qsum : part + ps};
-            if (p.qsplit) jobs[njobs++] = {1, PL_QH, -1, part + 2 * ps, nullptr};
+            if (!reuse) {
+                if (p.qsplit)
+                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum ? p.tsum : part, p.qsum ? p.qsum : part + ps};
+                else
+                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum, p.qsum};
+            }
+            if (p.qsplit) jobs[njobs++] = {1, PL_QH, -1, nullptr, nullptr};
             break;
         default:  // STD_F
             if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum ? p.tsum : part, p.fsum ? p.fsum : part + 2 * ps};
-            jobs[njobs++] = {1, q_lo, p.qsplit ? PL_QH : -1, part + ps, p.qsplit ? part + 3 * ps : nullptr};
+            jobs[njobs++] = {1, q_lo, p.qsplit ? PL_QH : -1, nullptr, nullptr};
             break;
     }
     if (njobs > 0) {
@@ -1985,13 +2025,25 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
         }
         TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, X, tw)));
         TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
-        TOPO_LAUNCH("disc_fft_store", s, (dfft_store_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, scale)));
+        const dim3 sgrid(N, planes);
+        if (j + 1 < njobs) {
+            TOPO_LAUNCH("disc_fft_store", s, (dfft_store_kernel<N, -1><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale)));
+        } else {
+            switch (pl.mode) {
+                case TPI_I: TOPO_LAUNCH("disc_fft_finish<TPI_I>", s, (dfft_store_kernel<N, TPI_I><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale))); break;
+                case TPI_X: TOPO_LAUNCH("disc_fft_finish<TPI_X>", s, (dfft_store_kernel<N, TPI_X><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale))); break;
+                case STD_I: TOPO_LAUNCH("disc_fft_finish<STD_I>", s, (dfft_store_kernel<N, STD_I><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale))); break;
+                default: TOPO_LAUNCH("disc_fft_finish<STD_F>", s, (dfft_store_kernel<N, STD_F><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale))); break;
+            }
+        }
     }
-    switch (pl.mode) {
-        case TPI_I: TOPO_LAUNCH("disc_finish<TPI_I>", s, disc_finish_kernel<TPI_I><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
-        case TPI_X: TOPO_LAUNCH("disc_finish<TPI_X>", s, disc_finish_kernel<TPI_X><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
-        case STD_I: TOPO_LAUNCH("disc_finish<STD_I>", s, disc_finish_kernel<STD_I><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
-        default: TOPO_LAUNCH("disc_finish<STD_F>", s, disc_finish_kernel<STD_F><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
+    if (njobs == 0) {  // every plane sum was left by the other descriptor of the pair: finish only
+        switch (pl.mode) {
+            case TPI_I: TOPO_LAUNCH("disc_finish<TPI_I>", s, disc_finish_kernel<TPI_I><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
+            case TPI_X: TOPO_LAUNCH("disc_finish<TPI_X>", s, disc_finish_kernel<TPI_X><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
+            case STD_I: TOPO_LAUNCH("disc_finish<STD_I>", s, disc_finish_kernel<STD_I><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
+            default: TOPO_LAUNCH("disc_finish<STD_F>", s, disc_finish_kernel<STD_F><<<kNumSMs * 8, 256, 0, s>>>(p)); break;
+        }
     }
     return 0;
 }

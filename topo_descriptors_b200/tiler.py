@@ -73,7 +73,8 @@ class HostDEM:
 
     def rows(self, a, b):
         """Rows [a, b) as a contiguous float32 host array (float64 / lazy inputs are converted here, band by band)."""
-        return np.ascontiguousarray(np.asarray(self.src[a:b]), dtype=np.float32)
+        rows = np.ascontiguousarray(np.asarray(self.src[a:b]), dtype=np.float32)
+        return rows if rows.flags.writeable else rows.copy()  # (a read-only memmap view: torch wants a writable buffer)
 
     @property
     def stats(self):
