@@ -377,8 +377,9 @@ def run_gpu(args, rank, world, local_rank):
     value = n_calls * ny * nx / (ms_step * 1e-3) / 1e6
 
     # ---- per-kernel attribution of one more step (CUDA events around every launch, on its stream)
+    # (always eager: the launches inside a replayed graph are invisible to the per-launch events)
     _lib.profile_enable(True)
-    step()
+    bands.sweep(core, ctx, sizes, sigmas, res_x, res_y)
     torch.cuda.synchronize()
     prof = _lib.profile_dump()
     _lib.profile_enable(False)

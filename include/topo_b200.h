@@ -55,6 +55,12 @@ typedef struct topo_disc_cache {
     int valid;    /* in/out: bits 2k / 2k+1 = row prefix / column-side tables of plane kind k
                      (0 trunc(z) - tmin, 1 its square (or the low 16 bits of a split square), 2 fraction,
                      3 quantised elevation; the high half of a split square takes the next free kind) */
+    /* FFT route on float DEMs: the square plane travels alone in its complex transform, so the std of one size can
+     * bring home the square-plane sums of ANOTHER size in the idle imaginary half (two disc masks in one complex
+     * spectrum); that later std call then needs no transform of its own.  Optional: leave the three fields 0. */
+    unsigned long long* held; /* DEVICE, out_rows * nx uint64 owned by the caller for the life of the cache, or NULL */
+    int next_size;            /* in: the size of the next topo_std_f32 call with this cache (0 = none / unknown) */
+    int held_size;            /* in/out: the size whose square-plane sums `held` carries (0 = none); start with 0 */
 } topo_disc_cache;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -71,7 +77,8 @@ int topo_profile_dump(char* buf, size_t cap);
 /* Execution-shape switches, all on by default: "octagon" (octagon core of the shared-plane disc walk), "tiny"
  * (register sliding sums for sizes 5..13), "sx_tma" (TMA-staged Sx tile), "gauss_fft" (float64 FFT overlap-save for
  * wide Gaussian radii), "grad_fused" (single-kernel small-radius gradient), "disc_fft" (exact disc sums of sizes >= 128
- * by float64 FFT convolution of the integer planes instead of the prefix-plane walk).  Every setting gives the same results
+ * by float64 FFT convolution of the integer planes instead of the prefix-plane walk), "fft_tstore" (the first
+ * inverse pass of the 2-D FFT routes stores its lines transposed instead of running a transpose pass).  Every setting gives the same results
  * through another kernel shape (the tests flip them to compare shapes bit for bit); nothing is read from the
  * process environment.  Returns 0, or -1 for an unknown name. */
 int topo_set_option(const char* name, int value);

@@ -42,10 +42,15 @@ def test_tpi_std_401_801_inside_a_cached_sweep(terrain, kind):
     z = terrain[0] if kind == "float" else terrain[1]
     want = {s: (O.tpi_exact(z, s), O.std_exact(z, s)) for s in (401, 801)}
     shared = DeviceDEM(dev.to_device(z)).share_disc_planes(801)
-    dev.tpi(shared, 41), dev.std(shared, 41)  # a smaller size first: the planes are then laid out for 801, used by 41
-    for s in (401, 801):
-        assert maxdiff(dev.tpi(shared, s).cpu().numpy(), want[s][0]) <= TOL_M, (kind, s)
-        assert maxdiff(dev.std(shared, s).cpu().numpy(), want[s][1]) <= TOL_M, (kind, s)
+    # a smaller size first: the planes are then laid out for 801, used by 41.  Every std announces the next std size,
+    # as bands.sweep does: on the float DEM the square-plane sums of 401 ride in the transform of std(41), std(401) then
+    # has no transform to share and std(801) runs its own
+    dev.tpi(shared, 41), dev.std(shared, 41, next_size=401)
+    for s, nxt in ((401, 801), (801, 0)):
+        assert maxdiff(dev.tpi(shared, s, pair_std=True).cpu().numpy(), want[s][0]) <= TOL_M, (kind, s)
+        assert maxdiff(dev.std(shared, s, next_size=nxt).cpu().numpy(), want[s][1]) <= TOL_M, (kind, s)
+    if kind == "float":
+        assert shared._plane_cache[1].held_size == 401
     assert shared._plane_cache is not None and shared._plane_cache[1].valid != 0
     shared.release_disc_planes()
     assert maxdiff(topo.tpi(z, 801), want[801][0]) <= TOL_M
@@ -345,7 +350,7 @@ def test_sweep_graph_replay_equals_the_eager_sweep():
         bands.sweep(core, ctx, sizes, sigmas, rx, ry, sink=lambda n, i, t: want.__setitem__((n, i), t.clone()))
         sg.run(core, ctx, sizes, sigmas, rx, ry)
         torch.cuda.synchronize()
-        assert set(sg.outputs) == set(want) and sg.launches > 50
+        assert set(sg.outputs) == set(want) and sg.launches > 30
         for key, w in want.items():
             assert torch.equal(sg.outputs[key], w), (k, key)
 
@@ -390,3 +395,35 @@ def test_disc_fft_route_is_bit_identical_to_the_prefix_plane_walk():
     lo, hi, halo = 500, 900, 150
     band = DeviceDEM(whole.tensor[lo - halo : hi + halo].contiguous(), gny=1300, gy0=lo - halo, stats=whole.stats)
     assert bool((dev.std(band, 301, lo, hi - lo) == ref[lo:hi]).all())
+
+
+def test_std_sums_of_the_next_size_ride_in_the_idle_half_transform():
+    """Float DEMs on the FFT route: the square plane is alone in its complex transform, so a std call that knows the
+    next std size computes both sizes' square-plane sums at once (two disc masks in one spectrum) and the next call
+    only finishes.  Bit-identical to the calls without the announcement, whatever is announced -- the right next size,
+    a size that comes later, a size that never comes -- with and without paired tpi calls, and fewer launches."""
+    from topo_descriptors_b200 import _lib
+
+    z = fractal_dem(1300, 1500, seed=26)
+    sizes = [801, 241, 81, 161, 41]
+
+    def run(announce, pair):
+        d = DeviceDEM(dev.to_device(z)).share_disc_planes(801)
+        n0 = _lib.launch_count()
+        out = {}
+        for k, s in enumerate(sizes):
+            t = dev.tpi(d, s, pair_std=True).cpu().numpy() if pair else None
+            out[s] = (t, dev.std(d, s, next_size=announce[k]).cpu().numpy())
+        return out, _lib.launch_count() - n0
+
+    for pair in (True, False):
+        plain, n_plain = run([0] * 5, pair)
+        for announce in (sizes[1:] + [0], [161, 0, 0, 0, 0], [sizes[(k + 2) % 5] for k in range(5)], [999, 33, 801, 161, 41]):
+            got, n_got = run(announce, pair)
+            for s in sizes:
+                assert np.array_equal(got[s][1], plain[s][1]), (pair, announce, s)
+                if pair:
+                    assert np.array_equal(got[s][0], plain[s][0]), (pair, announce, s)
+            if announce[0] == sizes[1]:
+                assert n_got < n_plain, (n_got, n_plain)
+    assert maxdiff(plain[241][1], O.std_exact(z, 241)) <= TOL_M

@@ -128,21 +128,25 @@ struct DiscParams {
 
 // ---- span table: kernel row i -> (dxlo, dxhi) of its run of ones, as DEM column offsets ------------
 // out[y,x] = sum_{i,j} K[i,j] * d[y + c - i, x + c - j]
-__device__ __forceinline__ void kernel_row_span(const DiscParams& p, int i, int& dxlo, int& dxhi) {
-    int jlo, jhi;
-    if (p.square) {
+__device__ __forceinline__ void disc_row_columns(int k, int mid, int square, int i, int& jlo, int& jhi) {
+    if (square) {
         jlo = 0;
-        jhi = p.k - 1;
+        jhi = k - 1;
     } else {
-        int di = i - p.mid;
-        int rem = p.mid * p.mid - di * di;  // >= 0 for every row of the kernel
+        int di = i - mid;
+        int rem = mid * mid - di * di;  // >= 0 for every row of the kernel
         int w = (int)floorf(sqrtf((float)rem));
         while (w * w > rem) --w;
         while ((w + 1) * (w + 1) <= rem) ++w;
-        jlo = p.mid - w;
-        jhi = p.mid + w;
-        if (jhi > p.k - 1) jhi = p.k - 1;  // even sizes: the disc is clipped on the right/bottom
+        jlo = mid - w;
+        jhi = mid + w;
+        if (jhi > k - 1) jhi = k - 1;  // even sizes: the disc is clipped on the right/bottom
     }
+}
+
+__device__ __forceinline__ void kernel_row_span(const DiscParams& p, int i, int& dxlo, int& dxhi) {
+    int jlo, jhi;
+    disc_row_columns(p.k, p.mid, p.square, i, jlo, jhi);
     dxlo = p.c - jhi;
     dxhi = p.c - jlo;
 }
@@ -1286,25 +1290,38 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
 }
 
 // first forward pass of the disc mask (circular_kernel / the square of sizes < 5), placed so that scipy's "same" crop
-// of the true convolution lands on window offset (H, H)
+// of the true convolution lands on window offset (H, H).  A second disc (kb > 0) may ride in the imaginary part: the
+// transform is linear, so the spectrum is m^_a + i m^_b, and its product with the spectrum of ONE real plane inverts to
+// (plane * m_a) + i (plane * m_b) -- two sizes of the same plane in one inverse transform.
+struct DiscMask {
+    int k, c, mid, square;
+};
+
+__device__ __forceinline__ bool mask_row_columns(const DiscMask& m, int i, int& jlo, int& jhi) {
+    if (i < 0 || i >= m.k) return false;
+    disc_row_columns(m.k, m.mid, m.square, i, jlo, jhi);
+    return true;
+}
+
 template <int N>
 __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
-    dfft_fwd_disc_kernel(const DiscParams p, const DfftGeom g, double2* __restrict__ dst, const double2* __restrict__ tw) {
+    dfft_fwd_disc_kernel(const DiscMask ma, const DiscMask mb, const DfftGeom g, double2* __restrict__ dst,
+                         const double2* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
     const int line = blockIdx.x;
-    const int i = line - (g.H - p.c);  // kernel row
     double2* out = dst + (int64_t)line * N;
-    if (i < 0 || i >= p.k) {
+    int alo = 0, ahi = -1, blo = 0, bhi = -1;
+    const bool row_a = mask_row_columns(ma, line - (g.H - ma.c), alo, ahi);
+    const bool row_b = mb.k > 0 && mask_row_columns(mb, line - (g.H - mb.c), blo, bhi);
+    if (!row_a && !row_b) {
         for (int n = threadIdx.x; n < N; n += FftShape<N>::NT) out[n] = make_double2(0.0, 0.0);
         return;
     }
-    int dxlo, dxhi;
-    kernel_row_span(p, i, dxlo, dxhi);          // DEM column offsets c - j of the row's run of ones
-    const int jlo = p.c - dxhi, jhi = p.c - dxlo;
+    const int sa = g.H - ma.c, sb = g.H - mb.c;
     fft2d_forward_line<N>(buf, tw, threadIdx.x, [&](int n) -> double2 {
-        const int j = n - (g.H - p.c);
-        return make_double2((j >= jlo && j <= jhi) ? 1.0 : 0.0, 0.0);
+        const int ja = n - sa, jb = n - sb;
+        return make_double2((ja >= alo && ja <= ahi) ? 1.0 : 0.0, (jb >= blo && jb <= bhi) ? 1.0 : 0.0);
     }, out);
 }
 
@@ -1378,6 +1395,7 @@ struct DiscPlan {
     bool fft;
     DfftGeom fg;
     int fft_pairs;                  // plane pairs of this DEM class (1: integer-valued, 2: float or split squares)
+    bool dual_ok;                   // the lone square plane stays exact with two disc masks in one spectrum
     int fft_mb0;                    // the plane that rides with T in pair 0 (the same for every call on this DEM: the
                                     // cached spectrum of pair 0 is shared by tpi and std): F, Q, QL or none
     size_t fft_plane_bytes;         // one spectrum: tiles x T x T x 16
@@ -1419,7 +1437,9 @@ static long long disc_count(int k) {
 }
 
 constexpr int kCachedTwoPassMin = 41;  // measured on B200: tpi+std 13.4 -> 10.5 ms at size 41, 22.0 -> 12.8 ms at size 81
-constexpr size_t kFusedSmemBudget = 101 * 1024;  // keep >= 2 CTAs per SM; larger discs go two-pass
+constexpr size_t kFusedSmemBudget = 108 * 1024;  // keep 2 CTAs per SM (2 x (108 + 1) KB <= 228 KB); larger discs go two-pass.
+                                                 // (108, not 101: the three planes of a float std at size 21 need 104.9 KB --
+                                                 // 22.7 ms of prefix planes + walks otherwise)
 
 static int max_rb(int mode) { return (mode == TPI_Q || mode == TPI_I) ? 8 : 4; }
 static int narr_of(int mode) { return (mode == TPI_Q || mode == TPI_I) ? 1 : (mode == STD_F ? 3 : 2); }
@@ -1614,7 +1634,7 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
     // shared planes / spectra: laid out for the halo of the largest size of the sweep
     const int plane_halo = cache_size >= size ? cache_size / 2 : 0;
     const bool fft = fft_route(size, plane_halo > 0 ? plane_halo : size / 2, plane_halo > 0);
-    pl.fft = false;
+    pl.fft = false, pl.dual_ok = false;
     double vmax[3] = {0, 0, 0};  // largest value a plane element can take
     double vmax_qh = 0;
     int qsplit = 0;
@@ -1685,6 +1705,7 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
             // the square plane rides along with T (and is kept for a following std): split it exactly when std would
             if (!(span * half_q * half_q < kU32) || !dfft_exact(T, half_q * half_q, nb)) qsplit = half_q <= 65535.0 ? 1 : 0;
         }
+        pl.dual_ok = mode == STD_F && !qsplit && dfft_exact(T, vmax[1], 2.0 * nb);  // |m_a + i m_b|^2 <= 2 N
         pl.fft_mb0 = !all_integer ? PL_F : (half_q > 65535.0 ? -1 : (qsplit ? PL_QL : PL_Q));
         if (mode == TPI_X || mode == STD_F) {
             int Sf = ilog2_floor((double)p.fscale);
@@ -1941,7 +1962,7 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo
 template <int N>
 static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo_disc_cache* cache, unsigned char* ws) {
     using S = FftShape<N>;
-    const DiscParams& p = pl.p;
+    DiscParams p = pl.p;  // (a copy: the square-plane sums may be redirected to the cache's held buffer)
     const DfftGeom& g = pl.fg;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -1971,42 +1992,63 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
     const int64_t ps = p.partial_stride;
 
     // the plane pairs this descriptor needs: {mode a, mode b, destination a, destination b}
-    struct Job { int pair, ma, mb; unsigned long long *da, *db; };
+    struct Job { int pair, ma, mb; unsigned long long *da, *db; int dual; };
     Job jobs[2];
     int njobs = 0;
+    // float DEMs, whole squares: the square plane is alone in its transform.  Its sums for this size may already sit
+    // in cache->held (left by the std of an earlier size); otherwise this call can leave those of cache->next_size there.
+    const bool lone_q = pl.mode == STD_F && !p.qsplit && cache && cache->held;
+    const bool held_q = lone_q && cache->held_size == p.k;
+    int dual = 0;
+    if (lone_q && !held_q && cache->next_size != p.k && cache->next_size >= kDiscFftMinCached && cache->next_size <= cache->max_size &&
+        pl.dual_ok)
+        dual = cache->next_size;
+    if (held_q) p.qsum = cache->held;
     switch (pl.mode) {
         // (the LAST job finishes the descriptor in its store pass and only keeps raw sums a later call will reuse;
         // earlier jobs leave their sums in tsum / qsum / fsum or the workspace)
         case TPI_I:
-            if (!reuse) jobs[njobs++] = {0, PL_T, pl.fft_mb0, p.tsum, pl.fft_mb0 >= 0 ? p.qsum : nullptr};
+            if (!reuse) jobs[njobs++] = {0, PL_T, pl.fft_mb0, p.tsum, pl.fft_mb0 >= 0 ? p.qsum : nullptr, 0};
             break;
         case TPI_X:
-            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum, p.fsum};
+            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum, p.fsum, 0};
             break;
         case STD_I:
             if (!reuse) {
                 if (p.qsplit)
-                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum ? p.tsum : part, p.qsum ? p.qsum : part + ps};
+                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum ? p.tsum : part, p.qsum ? p.qsum : part + ps, 0};
                 else
-                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum, p.qsum};
+                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum, p.qsum, 0};
             }
-            if (p.qsplit) jobs[njobs++] = {1, PL_QH, -1, nullptr, nullptr};
+            if (p.qsplit) jobs[njobs++] = {1, PL_QH, -1, nullptr, nullptr, 0};
             break;
         default:  // STD_F
-            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum ? p.tsum : part, p.fsum ? p.fsum : part + 2 * ps};
-            jobs[njobs++] = {1, q_lo, p.qsplit ? PL_QH : -1, nullptr, nullptr};
+            if (!reuse) {
+                if (held_q)  // (the only transform of the call: it finishes the descriptor, the sums stay where a pair wants them)
+                    jobs[njobs++] = {0, PL_T, PL_F, p.tsum, p.fsum, 0};
+                else
+                    jobs[njobs++] = {0, PL_T, PL_F, p.tsum ? p.tsum : part, p.fsum ? p.fsum : part + 2 * ps, 0};
+            }
+            if (!held_q) jobs[njobs++] = {1, q_lo, p.qsplit ? PL_QH : -1, nullptr, dual ? cache->held : nullptr, dual};
             break;
     }
-    if (njobs > 0) {
-        TOPO_LAUNCH("disc_fft_twiddles", s, fft_twiddle_kernel<<<ceil_div(N, 256), 256, 0, s>>>(tw, N));
-        // spectrum of the disc mask
-        TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(p, g, K1, tw)));
+    // spectrum of the disc mask (dual_size > 0: a second disc in the imaginary part, see dfft_fwd_disc_kernel)
+    const DiscMask mask_a{p.k, p.c, p.mid, p.square};
+    int mask_built = -1;
+    auto build_mask = [&](int dual_size) -> int {
+        if (mask_built == dual_size) return 0;
+        const DiscMask mask_b{dual_size, dual_size > 0 ? (dual_size - 1) / 2 : 0, dual_size / 2, 0};
+        TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(mask_a, mask_b, g, K1, tw)));
         TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
         TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
-    }
+        mask_built = dual_size;
+        return 0;
+    };
+    if (njobs > 0) TOPO_LAUNCH("disc_fft_twiddles", s, fft_twiddle_kernel<<<ceil_div(N, 256), 256, 0, s>>>(tw, N));
     const double scale = 1.0 / ((double)N * (double)N);
     for (int j = 0; j < njobs; ++j) {
         const Job& job = jobs[j];
+        if (build_mask(job.dual)) return -2;
         double2* dhat;
         bool have = false;
         if (cache) {
@@ -2023,8 +2065,12 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
             TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(Y, dhat, tw)));
             if (cache) cache->valid |= 1 << (16 + job.pair);
         }
-        TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, X, tw)));
-        TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+        if (option_enabled(kOptFftTstore)) {  // pass 1 writes the rows the store pass reads, already transposed
+            TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N, true><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, Y, tw, 2 * g.H, 2 * g.H + g.V)));
+        } else {
+            TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N, false><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, X, tw, 0, N)));
+            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+        }
         const dim3 sgrid(N, planes);
         if (j + 1 < njobs) {
             TOPO_LAUNCH("disc_fft_store", s, (dfft_store_kernel<N, -1><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale)));
@@ -2037,6 +2083,7 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
             }
         }
     }
+    if (dual) cache->held_size = dual;  // (published after the launches succeeded)
     if (njobs == 0) {  // every plane sum was left by the other descriptor of the pair: finish only
         switch (pl.mode) {
             case TPI_I: TOPO_LAUNCH("disc_finish<TPI_I>", s, disc_finish_kernel<TPI_I><<<kNumSMs * 8, 256, 0, s>>>(p)); break;

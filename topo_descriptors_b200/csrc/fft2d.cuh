@@ -57,18 +57,28 @@ static __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     fft2d_forward_line<N>(buf, tw, threadIdx.x, [&](int n) { return __ldg(src + base + n); }, dst + base);
 }
 
-// first inverse pass: the line is the product of two spectra (a: [planes][N][N], k: [N][N], same for every plane)
-template <int N>
+// first inverse pass: the line is the product of two spectra (a: [planes][N][N], k: [N][N], same for every plane).
+// TS = false: dst[plane][line][n] (a transpose pass follows).  TS = true: the outputs n in [n_lo, n_hi) -- the only ones
+// the second pass will turn into pixels -- go straight to the transposed plane dst[plane][n][line]: 16-byte stores
+// 16 N bytes apart, whose partner halves come from the CTA of line + 1 in the same wave and merge in L2, so DRAM sees
+// whole sectors and the separate transpose pass (a read + a write of the plane) disappears.
+template <int N, bool TS>
 static __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     fft2d_inv_product_kernel(const double2* __restrict__ a, const double2* __restrict__ k, double2* __restrict__ dst,
-                             const double2* __restrict__ tw) {
+                             const double2* __restrict__ tw, int n_lo, int n_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
     const int64_t base = ((int64_t)blockIdx.y * N + blockIdx.x) * N;
     const double2* __restrict__ kk = k + (int64_t)blockIdx.x * N;
-    double2* out = dst + base;
+    double2* out = TS ? dst + (int64_t)blockIdx.y * N * N + blockIdx.x : dst + base;
     fft2d_inverse_line<N>(buf, tw, threadIdx.x, [&](int i) { return cmul(__ldg(a + base + i), __ldg(kk + i)); },
-                          [&](int n, double2 y) { out[n] = y; });
+                          [&](int n, double2 y) {
+                              if constexpr (TS) {
+                                  if (n >= n_lo && n < n_hi) out[(int64_t)n * N] = y;
+                              } else {
+                                  out[n] = y;
+                              }
+                          });
 }
 
 // [planes][n][n] complex transpose, 32 x 32 tiles
@@ -85,7 +95,8 @@ template <int N>
 static int fft2d_set_smem_attributes() {
     using S = FftShape<N>;
     TOPO_CUDA(cudaFuncSetAttribute(fft2d_fwd_cplx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-    TOPO_CUDA(cudaFuncSetAttribute(fft2d_inv_product_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+    TOPO_CUDA(cudaFuncSetAttribute((fft2d_inv_product_kernel<N, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+    TOPO_CUDA(cudaFuncSetAttribute((fft2d_inv_product_kernel<N, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
     return 0;
 }
 

@@ -248,8 +248,12 @@ static int vfft_run(const VfftGeom& g, const float* dem, int64_t ld_in, float* n
         TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
         TOPO_LAUNCH("valley_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
         // all tiles: D^ * K^ -> inverse along the rows' axis -> transpose -> inverse + fold
-        TOPO_LAUNCH("valley_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, X, tw)));
-        TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+        if (option_enabled(kOptFftTstore)) {  // pass 1 writes the window rows the fold pass reads, already transposed
+            TOPO_LAUNCH("valley_fft_inv", s, (fft2d_inv_product_kernel<N, true><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, Y, tw, g.HT + g.HB, g.HT + g.HB + g.V_y)));
+        } else {
+            TOPO_LAUNCH("valley_fft_inv", s, (fft2d_inv_product_kernel<N, false><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, X, tw, 0, N)));
+            TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+        }
         q.a = Y, q.angle_a = kp.angle_a, q.angle_b = kp.angle_b, q.has_b = kp.kb != nullptr;
         TOPO_LAUNCH("valley_fft_fold", s, (vfft_fold_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(q)));
     }
