@@ -77,8 +77,7 @@ int topo_profile_dump(char* buf, size_t cap);
 /* Execution-shape switches, all on by default: "octagon" (octagon core of the shared-plane disc walk), "tiny"
  * (register sliding sums for sizes 5..13), "sx_tma" (TMA-staged Sx tile), "gauss_fft" (float64 FFT overlap-save for
  * wide Gaussian radii), "grad_fused" (single-kernel small-radius gradient), "disc_fft" (exact disc sums of sizes >= 128
- * by float64 FFT convolution of the integer planes instead of the prefix-plane walk), "fft_tstore" (the first
- * inverse pass of the 2-D FFT routes stores its lines transposed instead of running a transpose pass).  Every setting gives the same results
+ * by float64 FFT convolution of the integer planes instead of the prefix-plane walk).  Every setting gives the same results
  * through another kernel shape (the tests flip them to compare shapes bit for bit); nothing is read from the
  * process environment.  Returns 0, or -1 for an unknown name. */
 int topo_set_option(const char* name, int value);

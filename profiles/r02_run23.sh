@@ -1,11 +1,11 @@
 #!/bin/bash
 # dual-mask std lookahead + transposed store: full GPU test suite + bench (no CPU leg)
 O=gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > $O/r02_pytest18.log 2>&1; tail -6 $O/r02_pytest17.log
-python bench.py --steps 3 --warmup 3 --no-cpu > $O/r02_bench18.json 2> $O/r02_bench18.err; echo "bench rc=$?"; tail -c 500 $O/r02_bench18.err
+timeout 1500 python -m pytest tests -m gpu -x -q > $O/r02_pytest23.log 2>&1; tail -6 $O/r02_pytest17.log
+python bench.py --steps 3 --warmup 3 --no-cpu > $O/r02_bench23.json 2> $O/r02_bench23.err; echo "bench rc=$?"; tail -c 500 $O/r02_bench23.err
 python - <<'PY'
 import json
-s=open('gpurun_out/r02_bench18.json').read()
+s=open('gpurun_out/r02_bench23.json').read()
 b=json.loads(s[s.index('{'):])
 print('float ms', b['ms_per_step'], 'int ms', b['extra']['sweep_integer_dem']['ms_per_step'], 'e2e', b['e2e']['value'], 'launches', b['gpu_launches'])
 for k,v in list(b['kernels'].items())[:40]: print(f"{k:34s} {v['launches']:3d} {v['ms']:8.2f} avg {v['avg_ms']:.3f}")

@@ -15,7 +15,7 @@ void count_launch(int n = 1);
 
 // Execution-path switches (topo_set_option): every setting computes the same results through a different kernel
 // shape; the tests flip them to cross-check the shapes bit for bit.  Never read from the environment.
-enum Option { kOptOctagon = 0, kOptTiny = 1, kOptSxTma = 2, kOptGaussFft = 3, kOptGradFused = 4, kOptDiscFft = 5, kOptFftTstore = 6, kOptCount = 7 };
+enum Option { kOptOctagon = 0, kOptTiny = 1, kOptSxTma = 2, kOptGaussFft = 3, kOptGradFused = 4, kOptDiscFft = 5, kOptCount = 6 };
 bool option_enabled(int opt);
 
 // Optional per-kernel timing (topo_profile_enable / topo_profile_dump): CUDA events recorded on the

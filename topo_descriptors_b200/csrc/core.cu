@@ -23,7 +23,7 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-static std::atomic<int> g_options[kOptCount] = {{1}, {1}, {1}, {1}, {1}, {1}, {1}};
+static std::atomic<int> g_options[kOptCount] = {{1}, {1}, {1}, {1}, {1}, {1}};
 bool option_enabled(int opt) { return opt >= 0 && opt < kOptCount && g_options[opt].load(std::memory_order_relaxed) != 0; }
 
 // ---- per-kernel timing ---------------------------------------------------------------------------
@@ -232,7 +232,7 @@ const char* topo_last_error(void) { return g_err; }
 long long topo_launch_count(void) { return g_launches.load(); }
 
 int topo_set_option(const char* name, int value) {
-    static const char* const names[kOptCount] = {"octagon", "tiny", "sx_tma", "gauss_fft", "grad_fused", "disc_fft", "fft_tstore"};
+    static const char* const names[kOptCount] = {"octagon", "tiny", "sx_tma", "gauss_fft", "grad_fused", "disc_fft"};
     TOPO_CHECK(name != nullptr, "null option name");
     for (int i = 0; i < kOptCount; ++i) {
         if (strcmp(name, names[i]) == 0) {

@@ -1346,7 +1346,7 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     const double2* __restrict__ in = src + ((int64_t)plane * N + line) * N;
     const int64_t base = (int64_t)(gy - p.out_gy0) * p.nx + ox0 - x_lo;
     float* orow = p.out + (int64_t)(gy - p.out_gy0) * p.ld_out + ox0 - x_lo;
-    fft2d_inverse_line<N>(buf, tw, threadIdx.x, [&](int i) { return __ldg(in + i); }, [&](int n, double2 y) {
+    fft2d_inverse_line_from<N>(buf, tw, threadIdx.x, in, [&](int n, double2 y) {
         if (n < x_lo || n >= x_hi) return;
         const unsigned long long va = (unsigned long long)llrint(y.x * scale), vb = (unsigned long long)llrint(y.y * scale);
         const int64_t idx = base + n;
@@ -2065,12 +2065,10 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
             TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(Y, dhat, tw)));
             if (cache) cache->valid |= 1 << (16 + job.pair);
         }
-        if (option_enabled(kOptFftTstore)) {  // pass 1 writes the rows the store pass reads, already transposed
-            TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N, true><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, Y, tw, 2 * g.H, 2 * g.H + g.V)));
-        } else {
-            TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N, false><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, X, tw, 0, N)));
-            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
-        }
+        // only the window rows the store pass turns into pixels travel through the first pass's stores and the transpose
+        const int ct0 = (2 * g.H) / 32, ct1 = ceil_div(2 * g.H + g.V, 32);
+        TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(planes, N), S::NT, S::SMEM, s>>>(dhat, K1, X, tw, ct0 * 32, ct1 * 32)));
+        TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<dim3(ct1 - ct0, N / 32, planes), dim3(32, 8), 0, s>>>(X, Y, N, ct0));
         const dim3 sgrid(N, planes);
         if (j + 1 < njobs) {
             TOPO_LAUNCH("disc_fft_store", s, (dfft_store_kernel<N, -1><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale)));

@@ -27,14 +27,20 @@ __device__ __forceinline__ void fft2d_forward_line(double2* buf, const double2* 
     for (int i = tid; i < N; i += NT) out[i] = buf[pad(i)];
 }
 
-// Inverse transform of one digit-reversed line: load_perm(i) = element at position i; every natural-order output n is
-// handed to store_out(n, value).  No 1/N.
-template <int N, class LoadP, class Store>
-__device__ __forceinline__ void fft2d_inverse_line(double2* buf, const double2* __restrict__ tw, int tid, LoadP load_perm,
-                                                   Store store_out) {
+// 16-byte asynchronous global -> shared copy (LDGSTS, L1 bypassed): a whole line is put in flight by its CTA without
+// holding a register per element -- the synchronous load loop it replaces kept ONE load per thread in flight and paid the
+// DRAM latency sixteen times per line (ncu: long-scoreboard stalls 10-19 per issue, issue slots 18-35 % busy).
+__device__ __forceinline__ void cp_async_16(double2* smem_dst, const double2* __restrict__ gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Inverse stages of a line that already sits (digit-reversed, padded, synchronised) in `buf`; every natural-order
+// output n is handed to store_out(n, value).  No 1/N.
+template <int N, class Store>
+__device__ __forceinline__ void fft2d_inverse_staged(double2* buf, const double2* __restrict__ tw, int tid, Store store_out) {
     constexpr int NT = FftShape<N>::NT;
-    for (int i = tid; i < N; i += NT) buf[pad(i)] = load_perm(i);
-    __syncthreads();
     for (int u = tid; u < N / 8; u += NT) {
         double2 v[8];
 #pragma unroll
@@ -47,6 +53,51 @@ __device__ __forceinline__ void fft2d_inverse_line(double2* buf, const double2* 
     fft_inverse_outer<N>(buf, tw, tid, store_out);
 }
 
+// Inverse transform of one digit-reversed line: load_perm(i) = element at position i.
+template <int N, class LoadP, class Store>
+__device__ __forceinline__ void fft2d_inverse_line(double2* buf, const double2* __restrict__ tw, int tid, LoadP load_perm,
+                                                   Store store_out) {
+    constexpr int NT = FftShape<N>::NT;
+#pragma unroll 8
+    for (int i = tid; i < N; i += NT) buf[pad(i)] = load_perm(i);
+    __syncthreads();
+    fft2d_inverse_staged<N>(buf, tw, tid, store_out);
+}
+
+// ... of a line stored contiguously at src[0 .. N): staged with asynchronous copies, all in flight at once.
+template <int N, class Store>
+__device__ __forceinline__ void fft2d_inverse_line_from(double2* buf, const double2* __restrict__ tw, int tid,
+                                                        const double2* __restrict__ src, Store store_out) {
+    constexpr int NT = FftShape<N>::NT;
+#pragma unroll
+    for (int i = 0; i < N / NT; ++i) cp_async_16(buf + pad(tid + i * NT), src + tid + i * NT);
+    cp_async_wait_all();
+    __syncthreads();
+    fft2d_inverse_staged<N>(buf, tw, tid, store_out);
+}
+
+// ... of the product a[i] * k[i] of two contiguous lines: `a` arrives by asynchronous copies while the thread's own
+// k elements are loaded into registers; every thread then multiplies the elements it copied, in place.
+template <int N, class Store>
+__device__ __forceinline__ void fft2d_inverse_line_product(double2* buf, const double2* __restrict__ tw, int tid,
+                                                           const double2* __restrict__ a, const double2* __restrict__ k,
+                                                           Store store_out) {
+    constexpr int NT = FftShape<N>::NT, PER = N / NT;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) cp_async_16(buf + pad(tid + i * NT), a + tid + i * NT);
+    double2 kr[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) kr[i] = __ldg(k + tid + i * NT);
+    cp_async_wait_all();  // (the thread's own copies: no barrier needed before it touches them)
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        double2* e = buf + pad(tid + i * NT);
+        *e = cmul(*e, kr[i]);
+    }
+    __syncthreads();
+    fft2d_inverse_staged<N>(buf, tw, tid, store_out);
+}
+
 // second forward pass (and the first one of complex data): [planes][N][N] natural order -> digit-reversed lines
 template <int N>
 static __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
@@ -57,35 +108,33 @@ static __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     fft2d_forward_line<N>(buf, tw, threadIdx.x, [&](int n) { return __ldg(src + base + n); }, dst + base);
 }
 
-// first inverse pass: the line is the product of two spectra (a: [planes][N][N], k: [N][N], same for every plane).
-// TS = false: dst[plane][line][n] (a transpose pass follows).  TS = true: the outputs n in [n_lo, n_hi) -- the only ones
-// the second pass will turn into pixels -- go straight to the transposed plane dst[plane][n][line]: 16-byte stores
-// 16 N bytes apart, whose partner halves come from the CTA of line + 1 in the same wave and merge in L2, so DRAM sees
-// whole sectors and the separate transpose pass (a read + a write of the plane) disappears.
-template <int N, bool TS>
+// first inverse pass: the line is the product of two spectra (a: [planes][N][N], k: [N][N], same for every plane);
+// dst[plane][line][n] for n in [n_lo, n_hi) -- the columns the transpose pass will carry over (multiples of 32).
+// (Storing the lines already transposed -- 16-byte stores N x 16 bytes apart, one per row -- was measured: the first
+// pass grows from 3.2 to 6.3 ms per 25 tiles of 4096^2, more than the 2.2 ms transpose pass it would replace.)
+template <int N>
 static __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     fft2d_inv_product_kernel(const double2* __restrict__ a, const double2* __restrict__ k, double2* __restrict__ dst,
                              const double2* __restrict__ tw, int n_lo, int n_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
-    const int64_t base = ((int64_t)blockIdx.y * N + blockIdx.x) * N;
-    const double2* __restrict__ kk = k + (int64_t)blockIdx.x * N;
-    double2* out = TS ? dst + (int64_t)blockIdx.y * N * N + blockIdx.x : dst + base;
-    fft2d_inverse_line<N>(buf, tw, threadIdx.x, [&](int i) { return cmul(__ldg(a + base + i), __ldg(kk + i)); },
-                          [&](int n, double2 y) {
-                              if constexpr (TS) {
-                                  if (n >= n_lo && n < n_hi) out[(int64_t)n * N] = y;
-                              } else {
-                                  out[n] = y;
-                              }
-                          });
+    // grid (planes, N): the planes of one line are neighbours in launch order, so the line of k they all multiply by is
+    // read from DRAM once and then served by L2 (with the planes outermost it came back from DRAM for every plane)
+    const int plane = blockIdx.x, line = blockIdx.y;
+    const int64_t base = ((int64_t)plane * N + line) * N;
+    double2* out = dst + base;
+    fft2d_inverse_line_product<N>(buf, tw, threadIdx.x, a + base, k + (int64_t)line * N, [&](int n, double2 y) {
+        if (n >= n_lo && n < n_hi) out[n] = y;
+    });
 }
 
-// [planes][n][n] complex transpose, 32 x 32 tiles
-static __global__ void __launch_bounds__(256) fft2d_transpose_kernel(const double2* __restrict__ in, double2* __restrict__ out, int n) {
+// [planes][n][n] complex transpose, 32 x 32 tiles; blockIdx.x counts column tiles from col_tile0 (a caller that only
+// needs some rows of the result transposes only those columns of the source)
+static __global__ void __launch_bounds__(256) fft2d_transpose_kernel(const double2* __restrict__ in, double2* __restrict__ out, int n,
+                                                                     int col_tile0 = 0) {
     __shared__ double2 t[32][33];
     const int64_t base = (int64_t)blockIdx.z * n * n;
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int c0 = (blockIdx.x + col_tile0) * 32, r0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += 8) t[i][threadIdx.x] = __ldg(in + base + (int64_t)(r0 + i) * n + c0 + threadIdx.x);
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += 8) out[base + (int64_t)(c0 + i) * n + r0 + threadIdx.x] = t[threadIdx.x][i];
@@ -95,8 +144,7 @@ template <int N>
 static int fft2d_set_smem_attributes() {
     using S = FftShape<N>;
     TOPO_CUDA(cudaFuncSetAttribute(fft2d_fwd_cplx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-    TOPO_CUDA(cudaFuncSetAttribute((fft2d_inv_product_kernel<N, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-    TOPO_CUDA(cudaFuncSetAttribute((fft2d_inv_product_kernel<N, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+    TOPO_CUDA(cudaFuncSetAttribute(fft2d_inv_product_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
     return 0;
 }
 

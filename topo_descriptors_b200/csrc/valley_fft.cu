@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3) vfft_fold_
     const int x_hi = x_lo + min(g.V_x, g.nx - ox0);
     float* nrow = p.norm + (int64_t)(gy - g.out_gy0) * p.ld_out + ox0 - x_lo;
     float* drow = p.dir + (int64_t)(gy - g.out_gy0) * p.ld_out + ox0 - x_lo;
-    fft2d_inverse_line<N>(buf, p.tw, tid, [&](int i) { return __ldg(src + i); }, [&](int n, double2 y) {
+    fft2d_inverse_line_from<N>(buf, p.tw, tid, src, [&](int n, double2 y) {
         if (n < x_lo || n >= x_hi) return;
         float best = nrow[n], bdir = drow[n];
         const float va = (float)(y.x * p.scale);
@@ -248,12 +248,10 @@ static int vfft_run(const VfftGeom& g, const float* dem, int64_t ld_in, float* n
         TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
         TOPO_LAUNCH("valley_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
         // all tiles: D^ * K^ -> inverse along the rows' axis -> transpose -> inverse + fold
-        if (option_enabled(kOptFftTstore)) {  // pass 1 writes the window rows the fold pass reads, already transposed
-            TOPO_LAUNCH("valley_fft_inv", s, (fft2d_inv_product_kernel<N, true><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, Y, tw, g.HT + g.HB, g.HT + g.HB + g.V_y)));
-        } else {
-            TOPO_LAUNCH("valley_fft_inv", s, (fft2d_inv_product_kernel<N, false><<<dim3(N, planes), S::NT, S::SMEM, s>>>(dhat, K1, X, tw, 0, N)));
-            TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
-        }
+        // (only the window rows the fold pass uses travel through the first pass's stores and the transpose)
+        const int ct0 = (g.HT + g.HB) / 32, ct1 = ceil_div(g.HT + g.HB + g.V_y, 32);
+        TOPO_LAUNCH("valley_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(planes, N), S::NT, S::SMEM, s>>>(dhat, K1, X, tw, ct0 * 32, ct1 * 32)));
+        TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<dim3(ct1 - ct0, N / 32, planes), dim3(32, 8), 0, s>>>(X, Y, N, ct0));
         q.a = Y, q.angle_a = kp.angle_a, q.angle_b = kp.angle_b, q.has_b = kp.kb != nullptr;
         TOPO_LAUNCH("valley_fft_fold", s, (vfft_fold_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(q)));
     }
