@@ -273,7 +273,10 @@ def ncu_dram_ratio(kernel_name):
     .meta.json with the pixel count of the captured launch."""
     base = kernel_name.split("<")[0]
     sass_name = {"disc_hybrid": "disc_span_kernel", "disc_span": "disc_span_kernel", "grad_from_smooth": "gradient_kernel<0>",
-                 "sobel_gradient": "gradient_kernel<1>", "valley_bank": "valley_kernel"}.get(base, base + "_kernel")
+                 "sobel_gradient": "gradient_kernel<1>", "valley_bank": "valley_kernel", "disc_fft_inv": "fft2d_inv_product_kernel",
+                 "disc_fft_finish": "dfft_store_kernel", "disc_fft_store": "dfft_store_kernel",
+                 "disc_fft_transpose": "fft2d_transpose_kernel", "disc_fft_planes": "dfft_fwd_planes_kernel",
+                 "disc_fft_fwd": "fft2d_fwd_cplx_kernel", "gauss_fft": "fft_conv_kernel"}.get(base, base + "_kernel")
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*summary.csv")), reverse=True):
         meta = path.replace(".csv", ".meta.json")
         if not os.path.exists(meta):
@@ -620,12 +623,17 @@ def run_gpu(args, rank, world, local_rank):
     tile_T, tile_H = 4096, max(sizes) // 2
     tile_V = tile_T - 2 * tile_H
     spec = (-(-ctx.rows // tile_V)) * (-(-nx // tile_V)) * tile_T * tile_T * 16.0 / band_px
-    moved = {"disc_fft_inv": 2 * spec, "disc_fft_store": spec + 16, "disc_fft_planes": 4 + spec, "disc_finish<STD_F>": 28,
-             "disc_finish<TPI_X>": 24, "disc_finish<STD_I>": 20, "disc_finish<TPI_I>": 16, "gauss_fft": 8, "transpose": 8}
+    keep = tile_V / tile_T  # share of a first-pass line the second pass needs (the rest is neither stored nor transposed)
+    moved = {"disc_fft_inv": (1 + keep) * spec, "disc_fft_store": keep * spec + 16, "disc_fft_planes": 4 + spec,
+             "disc_fft_finish<TPI_X>": keep * spec + 4, "disc_fft_finish<STD_F>": keep * spec + 20,
+             "disc_fft_finish<TPI_I>": keep * spec + 4, "disc_fft_finish<STD_I>": keep * spec + 12,
+             "disc_finish<STD_F>": 28, "disc_finish<TPI_X>": 24, "disc_finish<STD_I>": 20, "disc_finish<TPI_I>": 16,
+             "gauss_fft": 8, "transpose": 8}
     memory_bound = {}
     for k, v in kernels.items():
         if not k.startswith(("stats_partial", "grad_from_smooth", "sobel_gradient", "gauss_grad_fused", "disc_tiny", "disc_prefix",
-                             "transpose", "disc_finish", "disc_fft_inv", "disc_fft_store", "disc_fft_planes", "gauss_fft")) or \
+                             "transpose", "disc_finish", "disc_fft_inv", "disc_fft_store", "disc_fft_finish", "disc_fft_planes",
+                             "gauss_fft")) or \
                 k.startswith(("gauss_fft_", )):
             continue
         e = {"GBps_alg": v["avg_GBps_alg"], "frac_of_hbm_peak": round(v["avg_GBps_alg"] / peak, 3)}
