@@ -1240,7 +1240,7 @@ __global__ void __launch_bounds__(256) disc_finish_kernel(const DiscParams p) {
 // window reproduces it with an absolute error far below 1/2 (bound checked by the planner: ~1e-14 * T * max value *
 // sqrt(N)), and rounding to the nearest integer gives EXACTLY the sums the prefix-plane walk accumulates -- the same
 // float64 epilogue then yields bit-identical TPI / STD.  Cost: one inverse 2-D transform per size and plane PAIR (two
-// planes ride in the real and imaginary parts), independent of the size: 12.6 ms per pair at 16384^2 against 29-34 ms
+// planes ride in the real and imaginary parts), independent of the size: 8.3 ms per pair at 16384^2 against 29-34 ms
 // per plane for the size-801 walk.  The forward transforms of the planes are shared by all sizes of a sweep (cache).
 struct DfftGeom {
     int T, H, V, tiles_y, tiles_x;  // transform length, window halo, outputs per tile edge
@@ -1402,7 +1402,7 @@ struct DiscPlan {
     size_t off_tw, off_dhat, off_x, off_y, off_k1, off_k2;
 };
 
-// Sizes from here take the FFT route (one inverse 2-D transform per plane pair, ~9.7 ms per pair at 16384^2 whatever the
+// Sizes from here take the FFT route (one inverse 2-D transform per plane pair, ~8.3 ms per pair at 16384^2 whatever the
 // size; a single call also pays the forward transforms of its planes).  Measured crossovers on B200: the cached octagon
 // walk costs 4.4 / 5.6 / 8.5 ms per PLANE at sizes 41 / 81 / 161 plus ~9 ms of table builds per plane kind and sweep.
 constexpr int kDiscFftMin = 128;        // single calls
