@@ -126,11 +126,37 @@ __device__ void block_reduce_store(StatsAcc a, double* dst) {
     }
 }
 
+// Per-thread accumulator of the hot loop: float min / max (FMNMX), 32-bit counters (a thread sees far fewer than 2^31
+// cells) and only the two sums in float64 -- the all-double StatsAcc made the pass issue-bound at 43 % of the HBM rate.
+// Same values in the same order: converted to a StatsAcc before the (fixed-order) reductions.
+struct StatsLane {
+    float mn = INFINITY, mx = -INFINITY;
+    unsigned nonfinite = 0, nonint = 0, n = 0;
+    double sum = 0.0, sumsq = 0.0;
+    __device__ __forceinline__ void add(float z) {
+        const bool ok = fabsf(z) < INFINITY;  // false for NaN too
+        const float zf = ok ? z : 0.f;
+        const double d = (double)zf;
+        mn = ok ? fminf(mn, z) : mn;
+        mx = ok ? fmaxf(mx, z) : mx;
+        sum += d;  // (+ 0.0 for a non-finite cell: exact, as if skipped)
+        sumsq = fma(d, d, sumsq);
+        nonint += (ok && truncf(z) != z) ? 1u : 0u;
+        nonfinite += ok ? 0u : 1u;
+        ++n;
+    }
+    __device__ StatsAcc widen() const {
+        StatsAcc a;
+        a.mn = (double)mn, a.mx = (double)mx, a.nonfinite = (double)nonfinite, a.nonint = (double)nonint;
+        a.sum = sum, a.sumsq = sumsq, a.n = (double)n;
+        return a;
+    }
+};
+
 __global__ void __launch_bounds__(kStatsThreads) stats_partial_kernel(const float* __restrict__ dem,
                                                                       int rows, int nx, int64_t ld,
                                                                       double* __restrict__ partials) {
-    StatsAcc a;
-    a.init();
+    StatsLane a;
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(dem) & 15) == 0);
     for (int y = blockIdx.x; y < rows; y += gridDim.x) {
         const float* row = dem + (int64_t)y * ld;
@@ -145,7 +171,7 @@ __global__ void __launch_bounds__(kStatsThreads) stats_partial_kernel(const floa
             for (int x = threadIdx.x; x < nx; x += kStatsThreads) a.add(__ldg(row + x));
         }
     }
-    block_reduce_store(a, partials + (int64_t)blockIdx.x * kStatsFields);
+    block_reduce_store(a.widen(), partials + (int64_t)blockIdx.x * kStatsFields);
 }
 
 __global__ void __launch_bounds__(kStatsThreads) stats_final_kernel(const double* __restrict__ partials,

@@ -2040,7 +2040,7 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
         const DiscMask mask_b{dual_size, dual_size > 0 ? (dual_size - 1) / 2 : 0, dual_size / 2, 0};
         TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(mask_a, mask_b, g, K1, tw)));
         TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
-        TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
+        TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N, true><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
         mask_built = dual_size;
         return 0;
     };

@@ -10,7 +10,10 @@ namespace topo {
 
 // Forward transform of one line: load_in(n) = sample n (natural order); the digit-reversed spectrum goes to
 // out[0 .. N) with coalesced stores.
-template <int N, class Load>
+// BY8: position i goes to out[(i & 7) * (N / 8) + (i >> 3)] -- the order in which the first inverse stage of
+// fft2d_inverse_line_product wants the multiplier line (thread u owns positions 8u .. 8u+7: with this order its eight
+// loads are coalesced across the threads).
+template <int N, bool BY8 = false, class Load>
 __device__ __forceinline__ void fft2d_forward_line(double2* buf, const double2* __restrict__ tw, int tid, Load load_in,
                                                    double2* __restrict__ out) {
     constexpr int NT = FftShape<N>::NT;
@@ -24,7 +27,11 @@ __device__ __forceinline__ void fft2d_forward_line(double2* buf, const double2* 
         for (int q = 0; q < 8; ++q) buf[pad(8 * u + q)] = v[q];
     }
     __syncthreads();
-    for (int i = tid; i < N; i += NT) out[i] = buf[pad(i)];
+    if constexpr (BY8) {
+        for (int i = tid; i < N; i += NT) out[i] = buf[pad((i % (N / 8)) * 8 + i / (N / 8))];  // out[q * N/8 + u] = position 8u + q
+    } else {
+        for (int i = tid; i < N; i += NT) out[i] = buf[pad(i)];
+    }
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS, L1 bypassed): a whole line is put in flight by its CTA without
@@ -76,39 +83,50 @@ __device__ __forceinline__ void fft2d_inverse_line_from(double2* buf, const doub
     fft2d_inverse_staged<N>(buf, tw, tid, store_out);
 }
 
-// ... of the product a[i] * k[i] of two contiguous lines: `a` arrives by asynchronous copies while the thread's own
-// k elements are loaded into registers; every thread then multiplies the elements it copied, in place.
+// ... of the product a[i] * k[i] of two lines: `a` (contiguous) arrives by asynchronous copies; the multiplier line is
+// stored by eights (k8[q * N/8 + u] = k[8u + q], see fft2d_forward_line<BY8>) so that every thread fetches the eight
+// factors of its first butterfly with coalesced loads and applies them in registers on the way into the first stage.
 template <int N, class Store>
 __device__ __forceinline__ void fft2d_inverse_line_product(double2* buf, const double2* __restrict__ tw, int tid,
-                                                           const double2* __restrict__ a, const double2* __restrict__ k,
+                                                           const double2* __restrict__ a, const double2* __restrict__ k8,
                                                            Store store_out) {
     constexpr int NT = FftShape<N>::NT, PER = N / NT;
 #pragma unroll
     for (int i = 0; i < PER; ++i) cp_async_16(buf + pad(tid + i * NT), a + tid + i * NT);
-    double2 kr[PER];
+    double2 kr[8];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) kr[i] = __ldg(k + tid + i * NT);
-    cp_async_wait_all();  // (the thread's own copies: no barrier needed before it touches them)
+    for (int q = 0; q < 8; ++q) kr[q] = __ldg(k8 + q * (N / 8) + tid);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int u = tid; u < N / 8; u += NT) {
+        double2 v[8];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        double2* e = buf + pad(tid + i * NT);
-        *e = cmul(*e, kr[i]);
+        for (int q = 0; q < 8; ++q) v[q] = cmul(buf[pad(8 * u + q)], kr[q]);
+        if (u + NT < N / 8) {  // the next butterfly's factors travel while this one is computed
+#pragma unroll
+            for (int q = 0; q < 8; ++q) kr[q] = __ldg(k8 + q * (N / 8) + u + NT);
+        }
+        dft8<true>(v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) buf[pad(8 * u + q)] = v[q];
     }
     __syncthreads();
-    fft2d_inverse_staged<N>(buf, tw, tid, store_out);
+    fft_inverse_outer<N>(buf, tw, tid, store_out);
 }
 
 // second forward pass (and the first one of complex data): [planes][N][N] natural order -> digit-reversed lines
-template <int N>
+// (BY8: the lines of a multiplier spectrum, in the order fft2d_inverse_line_product reads them)
+template <int N, bool BY8 = false>
 static __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     fft2d_fwd_cplx_kernel(const double2* __restrict__ src, double2* __restrict__ dst, const double2* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
     const int64_t base = ((int64_t)blockIdx.y * N + blockIdx.x) * N;
-    fft2d_forward_line<N>(buf, tw, threadIdx.x, [&](int n) { return __ldg(src + base + n); }, dst + base);
+    fft2d_forward_line<N, BY8>(buf, tw, threadIdx.x, [&](int n) { return __ldg(src + base + n); }, dst + base);
 }
 
-// first inverse pass: the line is the product of two spectra (a: [planes][N][N], k: [N][N], same for every plane);
+// first inverse pass: the line is the product of two spectra (a: [planes][N][N], k: [N][N] with its lines stored by
+// eights, same for every plane);
 // dst[plane][line][n] for n in [n_lo, n_hi) -- the columns the transpose pass will carry over (multiples of 32).
 // (Storing the lines already transposed -- 16-byte stores N x 16 bytes apart, one per row -- was measured: the first
 // pass grows from 3.2 to 6.3 ms per 25 tiles of 4096^2, more than the 2.2 ms transpose pass it would replace.)
@@ -143,7 +161,8 @@ static __global__ void __launch_bounds__(256) fft2d_transpose_kernel(const doubl
 template <int N>
 static int fft2d_set_smem_attributes() {
     using S = FftShape<N>;
-    TOPO_CUDA(cudaFuncSetAttribute(fft2d_fwd_cplx_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+    TOPO_CUDA(cudaFuncSetAttribute((fft2d_fwd_cplx_kernel<N, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+    TOPO_CUDA(cudaFuncSetAttribute((fft2d_fwd_cplx_kernel<N, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
     TOPO_CUDA(cudaFuncSetAttribute(fft2d_inv_product_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
     return 0;
 }

@@ -36,7 +36,7 @@ struct FftConvParams {
 
 // SETUP: transform the wrapped kernel h[n] = w[min(n, N - n)] (0 beyond lw) and store Re / N as the multiplier.
 template <int N, bool SETUP>
-__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3) fft_conv_kernel(const FftConvParams p) {
+__global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : (N <= 2048 ? 4 : 3)) fft_conv_kernel(const FftConvParams p) {
     using S = FftShape<N>;
     constexpr int NT = S::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -246,7 +246,7 @@ static int vfft_run(const VfftGeom& g, const float* dem, int64_t ld_in, float* n
         f.kp = kp, f.dst = K1;
         TOPO_LAUNCH("valley_fft_fwd", s, (vfft_fwd_kernel<N, VSRC_KERN><<<dim3(N, 1), S::NT, S::SMEM, s>>>(f)));
         TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
-        TOPO_LAUNCH("valley_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
+        TOPO_LAUNCH("valley_fft_fwd", s, (fft2d_fwd_cplx_kernel<N, true><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
         // all tiles: D^ * K^ -> inverse along the rows' axis -> transpose -> inverse + fold
         // (only the window rows the fold pass uses travel through the first pass's stores and the transpose)
         const int ct0 = (g.HT + g.HB) / 32, ct1 = ceil_div(g.HT + g.HB + g.V_y, 32);
