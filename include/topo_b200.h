@@ -55,12 +55,6 @@ typedef struct topo_disc_cache {
     int valid;    /* in/out: bits 2k / 2k+1 = row prefix / column-side tables of plane kind k
                      (0 trunc(z) - tmin, 1 its square (or the low 16 bits of a split square), 2 fraction,
                      3 quantised elevation; the high half of a split square takes the next free kind) */
-    /* FFT route on float DEMs: the square plane travels alone in its complex transform, so the std of one size can
-     * bring home the square-plane sums of ANOTHER size in the idle imaginary half (two disc masks in one complex
-     * spectrum); that later std call then needs no transform of its own.  Optional: leave the three fields 0. */
-    unsigned long long* held; /* DEVICE, out_rows * nx uint64 owned by the caller for the life of the cache, or NULL */
-    int next_size;            /* in: the size of the next topo_std_f32 call with this cache (0 = none / unknown) */
-    int held_size;            /* in/out: the size whose square-plane sums `held` carries (0 = none); start with 0 */
 } topo_disc_cache;
 
 /* ---- library ------------------------------------------------------------------------------ */

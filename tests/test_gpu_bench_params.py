@@ -42,15 +42,10 @@ def test_tpi_std_401_801_inside_a_cached_sweep(terrain, kind):
     z = terrain[0] if kind == "float" else terrain[1]
     want = {s: (O.tpi_exact(z, s), O.std_exact(z, s)) for s in (401, 801)}
     shared = DeviceDEM(dev.to_device(z)).share_disc_planes(801)
-    # a smaller size first: the planes are then laid out for 801, used by 41.  Every std announces the next std size,
-    # as bands.sweep does: on the float DEM the square-plane sums of 401 ride in the transform of std(41), std(401) then
-    # has no transform to share and std(801) runs its own
-    dev.tpi(shared, 41), dev.std(shared, 41, next_size=401)
-    for s, nxt in ((401, 801), (801, 0)):
+    dev.tpi(shared, 41), dev.std(shared, 41)  # a smaller size first: the planes are then laid out for 801, used by 41
+    for s in (401, 801):
         assert maxdiff(dev.tpi(shared, s, pair_std=True).cpu().numpy(), want[s][0]) <= TOL_M, (kind, s)
-        assert maxdiff(dev.std(shared, s, next_size=nxt).cpu().numpy(), want[s][1]) <= TOL_M, (kind, s)
-    if kind == "float":
-        assert shared._plane_cache[1].held_size == 401
+        assert maxdiff(dev.std(shared, s).cpu().numpy(), want[s][1]) <= TOL_M, (kind, s)
     assert shared._plane_cache is not None and shared._plane_cache[1].valid != 0
     shared.release_disc_planes()
     assert maxdiff(topo.tpi(z, 801), want[801][0]) <= TOL_M
@@ -358,8 +353,8 @@ def test_sweep_graph_replay_equals_the_eager_sweep():
 def test_disc_fft_route_is_bit_identical_to_the_prefix_plane_walk():
     """Sizes >= 128 compute their disc sums by float64 FFT convolution of the integer planes; the rounded sums are the
     exact integers the prefix-plane walk accumulates, so TPI and STD come out bit-identical: integer and float DEMs,
-    single calls and a cached sweep with tpi + std pairs, an even size, a wide range that splits the square plane, and
-    a row band."""
+    single calls and a cached sweep with tpi + std pairs, an even size, a wide range that splits the square plane,
+    planes that travel as twin tiles, and row bands."""
     from topo_descriptors_b200 import _lib
 
     def run(dem, sizes, hint=None, pair=False):
@@ -376,8 +371,14 @@ def test_disc_fft_route_is_bit_identical_to_the_prefix_plane_walk():
     zw = fractal_dem(900, 1000, seed=25, zmin=0.0, zmax=8848.0, integer=True)
     # (float DEMs: paired calls on both routes -- an unpaired float tpi walks the quantised plane, the FFT route always
     # carries the exact T + fraction pair)
+    # twin tiles (the lone square plane of a float DEM, the high half of split squares): several tiles per plane -- an
+    # even count (2 x 3 windows of 2048), an odd one (1 x 3: the last complex plane is half empty), a partial bottom tile
+    zt = fractal_dem(2048, 4000, seed=27)
+    zo = fractal_dem(1500, 4000, seed=28)
+    zwt = fractal_dem(1100, 4100, seed=29, zmin=0.0, zmax=8848.0, integer=True)
     cases = [(zi, [129, 200, 401], None, False), (z, [161, 301], None, True), (zi, [41, 161, 401, 801], 801, True),
-             (z, [81, 241, 801], 801, True), (zw, [401], None, False)]
+             (z, [81, 241, 801], 801, True), (zw, [401], None, False), (zt, [129, 161], None, True), (zo, [135, 65], 135, True),
+             (zwt, [201], None, False)]
     for dem, sizes, hint, pair in cases:
         got = run(dem, sizes, hint, pair)
         _lib.set_option("disc_fft", False)
@@ -395,37 +396,8 @@ def test_disc_fft_route_is_bit_identical_to_the_prefix_plane_walk():
     lo, hi, halo = 500, 900, 150
     band = DeviceDEM(whole.tensor[lo - halo : hi + halo].contiguous(), gny=1300, gy0=lo - halo, stats=whole.stats)
     assert bool((dev.std(band, 301, lo, hi - lo) == ref[lo:hi]).all())
-
-
-def test_std_sums_of_the_next_size_ride_in_the_idle_half_transform():
-    """Float DEMs on the FFT route: the square plane is alone in its complex transform, so a std call that knows the
-    next std size computes both sizes' square-plane sums at once (two disc masks in one spectrum) and the next call
-    only finishes.  Bit-identical to the calls without the announcement, whatever is announced -- the right next size,
-    a size that comes later, a size that never comes -- with and without paired tpi calls, and fewer launches."""
-    from topo_descriptors_b200 import _lib
-
-    z = fractal_dem(1300, 1500, seed=26)
-    sizes = [801, 241, 81, 161, 41]
-
-    def run(announce, pair):
-        d = DeviceDEM(dev.to_device(z)).share_disc_planes(801)
-        _lib.profile_enable(True)
-        out = {}
-        for k, s in enumerate(sizes):
-            t = dev.tpi(d, s, pair_std=True).cpu().numpy() if pair else None
-            out[s] = (t, dev.std(d, s, next_size=announce[k]).cpu().numpy())
-        transforms = _lib.profile_dump()["disc_fft_inv"]["launches"]  # inverse 2-D transforms of the run
-        _lib.profile_enable(False)
-        return out, transforms
-
-    for pair in (True, False):
-        plain, n_plain = run([0] * 5, pair)
-        for announce in (sizes[1:] + [0], [161, 0, 0, 0, 0], [sizes[(k + 2) % 5] for k in range(5)], [999, 33, 801, 161, 41]):
-            got, n_got = run(announce, pair)
-            for s in sizes:
-                assert np.array_equal(got[s][1], plain[s][1]), (pair, announce, s)
-                if pair:
-                    assert np.array_equal(got[s][0], plain[s][0]), (pair, announce, s)
-            if announce[0] == sizes[1]:  # 5 sizes: 2 of the 5 lone square-plane transforms disappear
-                assert (n_plain, n_got) == (10, 8), (n_plain, n_got)
-    assert maxdiff(plain[241][1], O.std_exact(z, 241)) <= TOL_M
+    whole = DeviceDEM(dev.to_device(zt))  # float DEM, twin tiles, band rows that end inside a tile
+    ref = dev.std(whole, 129)
+    lo, hi, halo = 300, 1750, 64
+    band = DeviceDEM(whole.tensor[lo - halo : hi + halo].contiguous(), gny=2048, gy0=lo - halo, stats=whole.stats)
+    assert bool((dev.std(band, 129, lo, hi - lo) == ref[lo:hi]).all())

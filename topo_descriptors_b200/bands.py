@@ -164,15 +164,14 @@ def _sweep_body(ddem, ctx, sizes, sigmas, res_x, res_y, what, sink):
     ry, ry2d = res_y
     # largest scales first: their kernels run for milliseconds, so the host gets ahead of the GPU right after the
     # statistics read-back instead of feeding it one short launch at a time (matters on thin bands: 8 GPUs)
-    order = sorted(enumerate(sizes), key=lambda e: -int(e[1]))
-    for pos, (i, size) in enumerate(order):
+    for i, size in sorted(enumerate(sizes), key=lambda e: -int(e[1])):
         if "tpi" in what:
             out = dev.tpi(ddem, size, ctx.r0, ctx.rows, pair_std="std" in what)
             calls += 1
             if sink:
                 sink("tpi", i, out)
         if "std" in what:
-            out = dev.std(ddem, size, ctx.r0, ctx.rows, next_size=order[pos + 1][1] if pos + 1 < len(order) else 0)
+            out = dev.std(ddem, size, ctx.r0, ctx.rows)
             calls += 1
             if sink:
                 sink("std", i, out)

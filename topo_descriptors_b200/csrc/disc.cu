@@ -1270,58 +1270,66 @@ __device__ __forceinline__ double plane_value_rt(const DiscParams& p, int mode, 
 }
 
 // first forward pass of a plane pair: window row `line` of tile `plane`; zero elevation outside the image (the
-// reference's zero padding: it converts to the planes' own "zero")
+// reference's zero padding: it converts to the planes' own "zero").
+// twin (a plane that travels alone, mode_b < 0): the imaginary part carries the SAME plane of ANOTHER tile -- complex
+// plane c holds tile 2c (real) and tile 2c + 1 (imaginary).  The disc mask is real, so the inverse transform of the
+// product returns the two tiles' disc sums in its real and imaginary parts: a lone plane costs half the transforms
+// (forward and inverse) and half the spectrum.
 template <int N>
 __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
-    dfft_fwd_planes_kernel(const DiscParams p, const DfftGeom g, int mode_a, int mode_b, double2* __restrict__ dst,
+    dfft_fwd_planes_kernel(const DiscParams p, const DfftGeom g, int mode_a, int mode_b, int twin, double2* __restrict__ dst,
                            const double2* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
     const int line = blockIdx.x, plane = blockIdx.y;
-    const int ty = plane / g.tiles_x, tx = plane - ty * g.tiles_x;
-    const int gy = p.out_gy0 + ty * g.V - g.H + line, c0 = tx * g.V - g.H;
-    const bool row_ok = gy >= 0 && gy < p.gny && gy >= p.in_gy0 && gy < p.in_gy0 + p.in_rows;
-    const float* row = p.dem + (int64_t)(row_ok ? gy - p.in_gy0 : 0) * p.ld_in;
+    const int ntiles = g.tiles_y * g.tiles_x;
+    const int tile_a = twin ? 2 * plane : plane, tile_b = 2 * plane + 1;
+    const float *row_a, *row_b = nullptr;
+    bool ok_a, ok_b = false;
+    int c0_a, c0_b = 0;
+    auto locate = [&](int tile, const float*& row, bool& ok, int& c0) {
+        const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+        const int gy = p.out_gy0 + ty * g.V - g.H + line;
+        c0 = tx * g.V - g.H;
+        ok = gy >= 0 && gy < p.gny && gy >= p.in_gy0 && gy < p.in_gy0 + p.in_rows;
+        row = p.dem + (int64_t)(ok ? gy - p.in_gy0 : 0) * p.ld_in;
+    };
+    locate(tile_a, row_a, ok_a, c0_a);
+    const bool have_b = twin && tile_b < ntiles;
+    if (have_b) locate(tile_b, row_b, ok_b, c0_b);
     fft2d_forward_line<N>(buf, tw, threadIdx.x, [&](int n) -> double2 {
-        const int gx = c0 + n;
-        const float z = (row_ok && gx >= 0 && gx < p.nx) ? __ldg(row + gx) : 0.f;
-        return make_double2(plane_value_rt(p, mode_a, z), mode_b >= 0 ? plane_value_rt(p, mode_b, z) : 0.0);
+        const int gx = c0_a + n;
+        const float z = (ok_a && gx >= 0 && gx < p.nx) ? __ldg(row_a + gx) : 0.f;
+        double im = 0.0;
+        if (have_b) {
+            const int gxb = c0_b + n;
+            im = plane_value_rt(p, mode_a, (ok_b && gxb >= 0 && gxb < p.nx) ? __ldg(row_b + gxb) : 0.f);
+        } else if (mode_b >= 0) {
+            im = plane_value_rt(p, mode_b, z);
+        }
+        return make_double2(plane_value_rt(p, mode_a, z), im);
     }, dst + ((int64_t)plane * N + line) * N);
 }
 
 // first forward pass of the disc mask (circular_kernel / the square of sizes < 5), placed so that scipy's "same" crop
-// of the true convolution lands on window offset (H, H).  A second disc (kb > 0) may ride in the imaginary part: the
-// transform is linear, so the spectrum is m^_a + i m^_b, and its product with the spectrum of ONE real plane inverts to
-// (plane * m_a) + i (plane * m_b) -- two sizes of the same plane in one inverse transform.
-struct DiscMask {
-    int k, c, mid, square;
-};
-
-__device__ __forceinline__ bool mask_row_columns(const DiscMask& m, int i, int& jlo, int& jhi) {
-    if (i < 0 || i >= m.k) return false;
-    disc_row_columns(m.k, m.mid, m.square, i, jlo, jhi);
-    return true;
-}
-
+// of the true convolution lands on window offset (H, H)
 template <int N>
 __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
-    dfft_fwd_disc_kernel(const DiscMask ma, const DiscMask mb, const DfftGeom g, double2* __restrict__ dst,
-                         const double2* __restrict__ tw) {
+    dfft_fwd_disc_kernel(const DiscParams p, const DfftGeom g, double2* __restrict__ dst, const double2* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
     const int line = blockIdx.x;
+    const int i = line - (g.H - p.c);  // kernel row
     double2* out = dst + (int64_t)line * N;
-    int alo = 0, ahi = -1, blo = 0, bhi = -1;
-    const bool row_a = mask_row_columns(ma, line - (g.H - ma.c), alo, ahi);
-    const bool row_b = mb.k > 0 && mask_row_columns(mb, line - (g.H - mb.c), blo, bhi);
-    if (!row_a && !row_b) {
+    if (i < 0 || i >= p.k) {
         for (int n = threadIdx.x; n < N; n += FftShape<N>::NT) out[n] = make_double2(0.0, 0.0);
         return;
     }
-    const int sa = g.H - ma.c, sb = g.H - mb.c;
+    int jlo, jhi;
+    disc_row_columns(p.k, p.mid, p.square, i, jlo, jhi);
     fft2d_forward_line<N>(buf, tw, threadIdx.x, [&](int n) -> double2 {
-        const int ja = n - sa, jb = n - sb;
-        return make_double2((ja >= alo && ja <= ahi) ? 1.0 : 0.0, (jb >= blo && jb <= bhi) ? 1.0 : 0.0);
+        const int j = n - (g.H - p.c);
+        return make_double2((j >= jlo && j <= jhi) ? 1.0 : 0.0, 0.0);
     }, out);
 }
 
@@ -1329,7 +1337,8 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
 // FIN < 0: store the raw sums of the pair.  FIN = descriptor mode: this is the LAST pair of the descriptor -- gather the
 // other planes' sums (left by an earlier pair of this call or by the tpi of a tpi + std pair) and finish in place, which
 // saves the 16 B/px round trip of the raw sums and the separate finish pass.
-template <int N, int FIN>
+// TWIN: the real and imaginary parts are the sums of plane mode_a on tiles 2c and 2c + 1 (see dfft_fwd_planes_kernel).
+template <int N, int FIN, bool TWIN>
 __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     dfft_store_kernel(const DiscParams p, const DfftGeom g, const double2* __restrict__ src, const double2* __restrict__ tw,
                       unsigned long long* __restrict__ dest_a, unsigned long long* __restrict__ dest_b, int mode_a, int mode_b,
@@ -1337,30 +1346,36 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
     const int line = blockIdx.x, plane = blockIdx.y;
-    const int ty = plane / g.tiles_x, tx = plane - ty * g.tiles_x;
-    const int oy0 = p.out_gy0 + ty * g.V;
-    const int gy = oy0 + line - 2 * g.H;
-    const int oy1 = min(oy0 + g.V, p.out_gy0 + p.out_rows);
-    if (gy < oy0 || gy >= oy1) return;  // CTA-uniform
-    const int ox0 = tx * g.V, x_lo = 2 * g.H, x_hi = x_lo + min(g.V, p.nx - ox0);
+    const int x_lo = 2 * g.H;
+    // output row / first column / column bound of a tile for this window line (row < 0: nothing to produce)
+    auto locate = [&](int tile, int& gy, int& ox0, int& x_hi) {
+        const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
+        const int oy0 = p.out_gy0 + ty * g.V;
+        const int oy1 = min(oy0 + g.V, p.out_gy0 + p.out_rows);
+        gy = oy0 + line - 2 * g.H;
+        if (tile >= g.tiles_y * g.tiles_x || gy < oy0 || gy >= oy1) gy = -1;
+        ox0 = tx * g.V;
+        x_hi = x_lo + min(g.V, p.nx - ox0);
+    };
+    int gy_a, ox_a, xh_a, gy_b = -1, ox_b = 0, xh_b = 0;
+    locate(TWIN ? 2 * plane : plane, gy_a, ox_a, xh_a);
+    if constexpr (TWIN) locate(2 * plane + 1, gy_b, ox_b, xh_b);
+    if (gy_a < 0 && gy_b < 0) return;  // CTA-uniform
     const double2* __restrict__ in = src + ((int64_t)plane * N + line) * N;
-    const int64_t base = (int64_t)(gy - p.out_gy0) * p.nx + ox0 - x_lo;
-    float* orow = p.out + (int64_t)(gy - p.out_gy0) * p.ld_out + ox0 - x_lo;
-    fft2d_inverse_line_from<N>(buf, tw, threadIdx.x, in, [&](int n, double2 y) {
-        if (n < x_lo || n >= x_hi) return;
-        const unsigned long long va = (unsigned long long)llrint(y.x * scale), vb = (unsigned long long)llrint(y.y * scale);
-        const int64_t idx = base + n;
+    // one output pixel: va / vb = this transform's sums of planes ma / mb at the pixel (mb < 0: none)
+    auto emit = [&](int gy, int x, unsigned long long va, unsigned long long vb, int ma, int mb) {
+        const int64_t idx = (int64_t)(gy - p.out_gy0) * p.nx + x;
         if (dest_a) dest_a[idx] = va;
-        if (dest_b) dest_b[idx] = vb;
+        if (mb >= 0 && dest_b) dest_b[idx] = vb;
         if constexpr (FIN >= 0) {
             constexpr int NARR = ModeTraits<FIN>::NARR;
             unsigned long long acc[NARR];
 #pragma unroll
             for (int a = 0; a < NARR; ++a) {
                 const int pm = a == 0 ? PL_T : (a == p.fplane ? PL_F : (p.qsplit ? PL_QL : PL_Q));  // the plane of slot a
-                if (pm == mode_a)
+                if (pm == ma)
                     acc[a] = va;
-                else if (pm == mode_b)
+                else if (pm == mb)
                     acc[a] = vb;
                 else
                     acc[a] = (a == 0 && p.tsum)          ? p.tsum[idx]
@@ -1370,9 +1385,19 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
             }
             if constexpr (FIN == STD_I || FIN == STD_F) {
                 if (p.qsplit)  // the high half of a split square plane: this pair's, or left by an earlier one
-                    acc[1] += (mode_a == PL_QH ? va : mode_b == PL_QH ? vb : p.partial[NARR * p.partial_stride + idx]) << 16;
+                    acc[1] += (ma == PL_QH ? va : mb == PL_QH ? vb : p.partial[NARR * p.partial_stride + idx]) << 16;
             }
-            orow[n] = finish<FIN>(p, acc, gy, ox0 - x_lo + n);
+            p.out[(int64_t)(gy - p.out_gy0) * p.ld_out + x] = finish<FIN>(p, acc, gy, x);
+        }
+    };
+    fft2d_inverse_line_from<N>(buf, tw, threadIdx.x, in, [&](int n, double2 y) {
+        if (n < x_lo) return;
+        const unsigned long long va = (unsigned long long)llrint(y.x * scale), vb = (unsigned long long)llrint(y.y * scale);
+        if constexpr (TWIN) {
+            if (gy_a >= 0 && n < xh_a) emit(gy_a, ox_a - x_lo + n, va, 0ull, mode_a, -1);
+            if (gy_b >= 0 && n < xh_b) emit(gy_b, ox_b - x_lo + n, vb, 0ull, mode_a, -1);
+        } else {
+            if (n < xh_a) emit(gy_a, ox_a - x_lo + n, va, vb, mode_a, mode_b);
         }
     });
 }
@@ -1395,7 +1420,6 @@ struct DiscPlan {
     bool fft;
     DfftGeom fg;
     int fft_pairs;                  // plane pairs of this DEM class (1: integer-valued, 2: float or split squares)
-    bool dual_ok;                   // the lone square plane stays exact with two disc masks in one spectrum
     int fft_mb0;                    // the plane that rides with T in pair 0 (the same for every call on this DEM: the
                                     // cached spectrum of pair 0 is shared by tpi and std): F, Q, QL or none
     size_t fft_plane_bytes;         // one spectrum: tiles x T x T x 16
@@ -1634,7 +1658,7 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
     // shared planes / spectra: laid out for the halo of the largest size of the sweep
     const int plane_halo = cache_size >= size ? cache_size / 2 : 0;
     const bool fft = fft_route(size, plane_halo > 0 ? plane_halo : size / 2, plane_halo > 0);
-    pl.fft = false, pl.dual_ok = false;
+    pl.fft = false;
     double vmax[3] = {0, 0, 0};  // largest value a plane element can take
     double vmax_qh = 0;
     int qsplit = 0;
@@ -1705,7 +1729,6 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
             // the square plane rides along with T (and is kept for a following std): split it exactly when std would
             if (!(span * half_q * half_q < kU32) || !dfft_exact(T, half_q * half_q, nb)) qsplit = half_q <= 65535.0 ? 1 : 0;
         }
-        pl.dual_ok = mode == STD_F && !qsplit && dfft_exact(T, vmax[1], 2.0 * nb);  // |m_a + i m_b|^2 <= 2 N
         pl.fft_mb0 = !all_integer ? PL_F : (half_q > 65535.0 ? -1 : (qsplit ? PL_QL : PL_Q));
         if (mode == TPI_X || mode == STD_F) {
             int Sf = ilog2_floor((double)p.fscale);
@@ -1962,7 +1985,7 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo
 template <int N>
 static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo_disc_cache* cache, unsigned char* ws) {
     using S = FftShape<N>;
-    DiscParams p = pl.p;  // (a copy: the square-plane sums may be redirected to the cache's held buffer)
+    const DiscParams& p = pl.p;
     const DfftGeom& g = pl.fg;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -1970,11 +1993,13 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
     if (dev >= 64 || !attr_set[dev]) {
         TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_planes_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
         TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_disc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, -1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, TPI_I>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, TPI_X>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_I>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_F>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, -1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, TPI_I, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, TPI_X, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_I, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_I, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
         if (fft2d_set_smem_attributes<N>()) return -2;
         if (dev < 64) attr_set[dev] = true;
     }
@@ -1983,72 +2008,55 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
     double2* Y = reinterpret_cast<double2*>(ws + pl.off_y);
     double2* K1 = reinterpret_cast<double2*>(ws + pl.off_k1);
     double2* K2 = reinterpret_cast<double2*>(ws + pl.off_k2);
-    const int planes = g.tiles_y * g.tiles_x;
-    TOPO_CHECK(planes <= 65535, "too many tiles for one launch: split the DEM in row bands");
-    const dim3 tgrid(N / 32, N / 32, planes), kgrid(N / 32, N / 32, 1);
+    const int tiles = g.tiles_y * g.tiles_x;
+    TOPO_CHECK(tiles <= 65535, "too many tiles for one launch: split the DEM in row bands");
+    const dim3 kgrid(N / 32, N / 32, 1);
     const bool reuse = tsum_op == 2;  // a previous call of the pair left the sums of plane pair 0 in tsum / qsum / fsum
     const int q_lo = p.qsplit ? PL_QL : PL_Q;
     unsigned long long* part = p.partial;
     const int64_t ps = p.partial_stride;
 
-    // the plane pairs this descriptor needs: {mode a, mode b, destination a, destination b}
-    struct Job { int pair, ma, mb; unsigned long long *da, *db; int dual; };
+    // the plane pairs this descriptor needs: {pair index, mode a, mode b, destination a, destination b}.
+    // A plane that travels alone in pair 1 (the squares of a float DEM, the high half of split squares) is laid out as
+    // twin tiles: two tiles of the same plane per complex plane (see dfft_fwd_planes_kernel).
+    struct Job { int pair, ma, mb; unsigned long long *da, *db; };
     Job jobs[2];
     int njobs = 0;
-    // float DEMs, whole squares: the square plane is alone in its transform.  Its sums for this size may already sit
-    // in cache->held (left by the std of an earlier size); otherwise this call can leave those of cache->next_size there.
-    const bool lone_q = pl.mode == STD_F && !p.qsplit && cache && cache->held;
-    const bool held_q = lone_q && cache->held_size == p.k;
-    int dual = 0;
-    if (lone_q && !held_q && cache->next_size != p.k && cache->next_size >= kDiscFftMinCached && cache->next_size <= cache->max_size &&
-        pl.dual_ok)
-        dual = cache->next_size;
-    if (held_q) p.qsum = cache->held;
     switch (pl.mode) {
         // (the LAST job finishes the descriptor in its store pass and only keeps raw sums a later call will reuse;
         // earlier jobs leave their sums in tsum / qsum / fsum or the workspace)
         case TPI_I:
-            if (!reuse) jobs[njobs++] = {0, PL_T, pl.fft_mb0, p.tsum, pl.fft_mb0 >= 0 ? p.qsum : nullptr, 0};
+            if (!reuse) jobs[njobs++] = {0, PL_T, pl.fft_mb0, p.tsum, pl.fft_mb0 >= 0 ? p.qsum : nullptr};
             break;
         case TPI_X:
-            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum, p.fsum, 0};
+            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum, p.fsum};
             break;
         case STD_I:
             if (!reuse) {
                 if (p.qsplit)
-                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum ? p.tsum : part, p.qsum ? p.qsum : part + ps, 0};
+                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum ? p.tsum : part, p.qsum ? p.qsum : part + ps};
                 else
-                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum, p.qsum, 0};
+                    jobs[njobs++] = {0, PL_T, q_lo, p.tsum, p.qsum};
             }
-            if (p.qsplit) jobs[njobs++] = {1, PL_QH, -1, nullptr, nullptr, 0};
+            if (p.qsplit) jobs[njobs++] = {1, PL_QH, -1, nullptr, nullptr};
             break;
         default:  // STD_F
-            if (!reuse) {
-                if (held_q)  // (the only transform of the call: it finishes the descriptor, the sums stay where a pair wants them)
-                    jobs[njobs++] = {0, PL_T, PL_F, p.tsum, p.fsum, 0};
-                else
-                    jobs[njobs++] = {0, PL_T, PL_F, p.tsum ? p.tsum : part, p.fsum ? p.fsum : part + 2 * ps, 0};
-            }
-            if (!held_q) jobs[njobs++] = {1, q_lo, p.qsplit ? PL_QH : -1, nullptr, dual ? cache->held : nullptr, dual};
+            if (!reuse) jobs[njobs++] = {0, PL_T, PL_F, p.tsum ? p.tsum : part, p.fsum ? p.fsum : part + 2 * ps};
+            jobs[njobs++] = {1, q_lo, p.qsplit ? PL_QH : -1, nullptr, nullptr};
             break;
     }
-    // spectrum of the disc mask (dual_size > 0: a second disc in the imaginary part, see dfft_fwd_disc_kernel)
-    const DiscMask mask_a{p.k, p.c, p.mid, p.square};
-    int mask_built = -1;
-    auto build_mask = [&](int dual_size) -> int {
-        if (mask_built == dual_size) return 0;
-        const DiscMask mask_b{dual_size, dual_size > 0 ? (dual_size - 1) / 2 : 0, dual_size / 2, 0};
-        TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(mask_a, mask_b, g, K1, tw)));
+    if (njobs > 0) {
+        TOPO_LAUNCH("disc_fft_twiddles", s, fft_twiddle_kernel<<<ceil_div(N, 256), 256, 0, s>>>(tw, N));
+        // spectrum of the disc mask (its lines stored by eights: the order the product pass reads them in)
+        TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(p, g, K1, tw)));
         TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
         TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N, true><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
-        mask_built = dual_size;
-        return 0;
-    };
-    if (njobs > 0) TOPO_LAUNCH("disc_fft_twiddles", s, fft_twiddle_kernel<<<ceil_div(N, 256), 256, 0, s>>>(tw, N));
+    }
     const double scale = 1.0 / ((double)N * (double)N);
     for (int j = 0; j < njobs; ++j) {
         const Job& job = jobs[j];
-        if (build_mask(job.dual)) return -2;
+        const bool twin = job.pair == 1 && job.mb < 0;
+        const int planes = twin ? (tiles + 1) / 2 : tiles;  // complex planes of this job
         double2* dhat;
         bool have = false;
         if (cache) {
@@ -2060,8 +2068,8 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
             dhat = reinterpret_cast<double2*>(ws + pl.off_dhat + (size_t)job.pair * pl.fft_plane_bytes);
         }
         if (!have) {
-            TOPO_LAUNCH("disc_fft_planes", s, (dfft_fwd_planes_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(p, g, job.ma, job.mb, X, tw)));
-            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+            TOPO_LAUNCH("disc_fft_planes", s, (dfft_fwd_planes_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(p, g, job.ma, job.mb, twin ? 1 : 0, X, tw)));
+            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<dim3(N / 32, N / 32, planes), dim3(32, 8), 0, s>>>(X, Y, N));
             TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(Y, dhat, tw)));
             if (cache) cache->valid |= 1 << (16 + job.pair);
         }
@@ -2070,18 +2078,28 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
         TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(planes, N), S::NT, S::SMEM, s>>>(dhat, K1, X, tw, ct0 * 32, ct1 * 32)));
         TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<dim3(ct1 - ct0, N / 32, planes), dim3(32, 8), 0, s>>>(X, Y, N, ct0));
         const dim3 sgrid(N, planes);
+#define TOPO_DFFT_STORE(LABEL, FIN, TWIN) \
+    TOPO_LAUNCH(LABEL, s, (dfft_store_kernel<N, FIN, TWIN><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale)))
         if (j + 1 < njobs) {
-            TOPO_LAUNCH("disc_fft_store", s, (dfft_store_kernel<N, -1><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale)));
+            TOPO_CHECK(!twin, "internal: a twin-tile job must be the last one of its descriptor");
+            TOPO_DFFT_STORE("disc_fft_store", -1, false);
+        } else if (twin) {
+            if (pl.mode == STD_I) {
+                TOPO_DFFT_STORE("disc_fft_finish<STD_I,twin>", STD_I, true);
+            } else {
+                TOPO_CHECK(pl.mode == STD_F, "internal: twin tiles outside std");
+                TOPO_DFFT_STORE("disc_fft_finish<STD_F,twin>", STD_F, true);
+            }
         } else {
             switch (pl.mode) {
-                case TPI_I: TOPO_LAUNCH("disc_fft_finish<TPI_I>", s, (dfft_store_kernel<N, TPI_I><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale))); break;
-                case TPI_X: TOPO_LAUNCH("disc_fft_finish<TPI_X>", s, (dfft_store_kernel<N, TPI_X><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale))); break;
-                case STD_I: TOPO_LAUNCH("disc_fft_finish<STD_I>", s, (dfft_store_kernel<N, STD_I><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale))); break;
-                default: TOPO_LAUNCH("disc_fft_finish<STD_F>", s, (dfft_store_kernel<N, STD_F><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale))); break;
+                case TPI_I: TOPO_DFFT_STORE("disc_fft_finish<TPI_I>", TPI_I, false); break;
+                case TPI_X: TOPO_DFFT_STORE("disc_fft_finish<TPI_X>", TPI_X, false); break;
+                case STD_I: TOPO_DFFT_STORE("disc_fft_finish<STD_I>", STD_I, false); break;
+                default: TOPO_DFFT_STORE("disc_fft_finish<STD_F>", STD_F, false); break;
             }
         }
+#undef TOPO_DFFT_STORE
     }
-    if (dual) cache->held_size = dual;  // (published after the launches succeeded)
     if (njobs == 0) {  // every plane sum was left by the other descriptor of the pair: finish only
         switch (pl.mode) {
             case TPI_I: TOPO_LAUNCH("disc_finish<TPI_I>", s, disc_finish_kernel<TPI_I><<<kNumSMs * 8, 256, 0, s>>>(p)); break;

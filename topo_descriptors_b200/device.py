@@ -69,7 +69,6 @@ class DeviceDEM:
         self.gy0 = int(gy0)
         self.gny = int(self.rows if gny is None else gny)
         self._stats = stats
-        self.next_std_size = 0  # set by a multi-scale driver before a std call: the size its next std call will use
 
     is_device_dem = True  # lets the Dataset container keep it as the values of the DEM variable
 
@@ -253,7 +252,7 @@ def _tsum_plan(dem, v, size, st, share, cache_size=0, pair=False):
     return t, 1, (key, t)
 
 
-def _disc(name, what, dem, size, out_gy0, out_rows, out, share, pair=False, next_size=0):
+def _disc(name, what, dem, size, out_gy0, out_rows, out, share, pair=False):
     torch = require_cuda()
     v = dem.view(out_gy0, out_rows)
     st = dem.stats
@@ -265,11 +264,6 @@ def _disc(name, what, dem, size, out_gy0, out_rows, out, share, pair=False, next
     L = _lib.load()
     cache = _plane_cache(dem, v, size, st)
     cache_size = cache.max_size if cache is not None else 0
-    if what == 1:
-        next_size = int(next_size or getattr(dem, "next_std_size", 0) or 0)
-        dem.next_std_size = 0
-        if cache is not None:
-            cache.next_size = next_size  # (the std that can ride along in this call's idle half transform)
     integer = 1 if st["nonint"] == 0 else 0
     # std of a float DEM reuses what a paired tpi left behind; it never starts a pair itself
     tsum, op, keep = _tsum_plan(dem, v, size, st, share, cache_size, pair or (what == 1 and getattr(dem, "_tsum", None) is not None))
@@ -317,15 +311,7 @@ def _plane_cache(dem, v, size, st):
     mem = _torch().empty(nbytes + 256, dtype=_torch().uint8, device=dem.tensor.device)
     base = (mem.data_ptr() + 255) & ~255
     cache = _lib.DiscCache(ctypes.c_void_p(base), nbytes, int(hint), 0)
-    held = None
-    if st["nonint"] > 0:
-        # float DEMs on the FFT route: room for the square-plane sums one std leaves for the next (topo_b200.h)
-        info = (ctypes.c_longlong * 20)()
-        ok = _lib.load().topo_disc_plan_info(ctypes.byref(v), int(hint), 1, 0, st["min"], st["max"], int(hint), 0, info)
-        if ok == 0 and info[17] and not info[16]:
-            held = _torch().empty((v.out_rows, dem.nx), dtype=_torch().int64, device=dem.tensor.device)
-            cache.held = ctypes.c_void_p(held.data_ptr())
-    dem._plane_cache = (key, cache, mem, held)  # `mem` / `held` keep the allocations alive
+    dem._plane_cache = (key, cache, mem)  # `mem` keeps the allocation alive
     return cache
 
 
@@ -338,11 +324,9 @@ def tpi(dem, size, out_gy0=None, out_rows=None, out=None, share=True, pair_std=F
     return _disc("topo_tpi_f32", 0, dem, size, out_gy0, out_rows, out, share, pair_std)
 
 
-def std(dem, size, out_gy0=None, out_rows=None, out=None, share=True, next_size=0):
-    """Device STD (float32; the host shim up-casts to float64 like the reference).  ``next_size``: inside a sweep
-    (``share_disc_planes``), the size of the next std call on this DEM -- on float DEMs its square-plane sums then
-    ride along in this call's transform and that call needs none of its own."""
-    return _disc("topo_std_f32", 1, dem, size, out_gy0, out_rows, out, share, next_size=next_size)
+def std(dem, size, out_gy0=None, out_rows=None, out=None, share=True):
+    """Device STD (float32; the host shim up-casts to float64 like the reference)."""
+    return _disc("topo_std_f32", 1, dem, size, out_gy0, out_rows, out, share)
 
 
 class _Res:

@@ -172,9 +172,9 @@ def sweep(dem, sizes, band_rows=None):
     def fn(d, r0, n):
         if len(sizes) > 1:
             d.share_disc_planes(max(sizes))
-        for k, s in enumerate(sizes):
+        for s in sizes:
             res[s][0][r0 : r0 + n] = dev.tpi(d, s, r0, n, pair_std=True).cpu().numpy()
-            res[s][1][r0 : r0 + n] = dev.std(d, s, r0, n, next_size=sizes[k + 1] if k + 1 < len(sizes) else 0).cpu().numpy()
+            res[s][1][r0 : r0 + n] = dev.std(d, s, r0, n).cpu().numpy()
         d.release_disc_planes()
         return []
 

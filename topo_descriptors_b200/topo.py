@@ -201,8 +201,6 @@ def compute_std(dem_ds, scales, smth_factors=None, ind_nans=[], crop=None, outdi
 
     for idx, scale_pxl in enumerate(scales_pxl):
         logger.info(f"Computing scale {scales[idx]} meters with smoothing factor {smth_factors[idx]} ...")
-        # (float DEMs inside a shared sweep: the next scale's square-plane sums ride along, see device.std)
-        ddem.next_std_size = int(scales_pxl[idx + 1]) if idx + 1 < len(scales_pxl) else 0
         out = std(ddem, scale_pxl, sigma=sigmas[idx])
         _finish_output(out, nans, dem_ds, _std_name(scales[idx], smth_factors[idx]), crop, outdir, "m",
                        dtype=np.float64)
