@@ -1362,6 +1362,35 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     if constexpr (TWIN) locate(2 * plane + 1, gy_b, ox_b, xh_b);
     if (gy_a < 0 && gy_b < 0) return;  // CTA-uniform
     const double2* __restrict__ in = src + ((int64_t)plane * N + line) * N;
+    if constexpr (FIN >= 0) {
+        // The epilogue reads, per pixel, the sums another pass left in HBM (and the DEM for TPI) right after the last
+        // butterfly stage, one dependent load per output: fetch those rows into L2 now, while the transform runs.
+        auto prefetch = [&](const void* base, int64_t first, int count, int elem) {
+            const char* b = reinterpret_cast<const char*>(base) + first * elem;
+            for (int64_t o = (int64_t)threadIdx.x * 128; o < (int64_t)count * elem; o += (int64_t)FftShape<N>::NT * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+        };
+        auto prefetch_row = [&](int gy, int ox0, int x_hi) {
+            if (gy < 0) return;
+            const int count = x_hi - x_lo;
+            const int64_t first = (int64_t)(gy - p.out_gy0) * p.nx + ox0;
+            constexpr int NARR = ModeTraits<FIN>::NARR;
+#pragma unroll
+            for (int a = 0; a < NARR; ++a) {
+                const int pm = a == 0 ? PL_T : (a == p.fplane ? PL_F : (p.qsplit ? PL_QL : PL_Q));
+                if (pm == mode_a || pm == mode_b) continue;
+                const unsigned long long* srcp = (a == 0 && p.tsum)          ? p.tsum
+                                                 : (a == p.fplane && p.fsum) ? p.fsum
+                                                 : (a == 1 && p.qsum)        ? p.qsum
+                                                                             : p.partial + a * p.partial_stride;
+                prefetch(srcp, first, count, 8);
+            }
+            if constexpr (FIN == TPI_I || FIN == TPI_X || FIN == TPI_Q)
+                prefetch(p.dem, (int64_t)(gy - p.in_gy0) * p.ld_in + ox0, count, 4);
+        };
+        prefetch_row(gy_a, ox_a, xh_a);
+        if constexpr (TWIN) prefetch_row(gy_b, ox_b, xh_b);
+    }
     // one output pixel: va / vb = this transform's sums of planes ma / mb at the pixel (mb < 0: none)
     auto emit = [&](int gy, int x, unsigned long long va, unsigned long long vb, int ma, int mb) {
         const int64_t idx = (int64_t)(gy - p.out_gy0) * p.nx + x;
