@@ -401,3 +401,31 @@ def test_disc_fft_route_is_bit_identical_to_the_prefix_plane_walk():
     lo, hi, halo = 300, 1750, 64
     band = DeviceDEM(whole.tensor[lo - halo : hi + halo].contiguous(), gny=2048, gy0=lo - halo, stats=whole.stats)
     assert bool((dev.std(band, 129, lo, hi - lo) == ref[lo:hi]).all())
+
+
+def test_tiny_disc_kernels_are_bit_identical_to_the_fused_kernel():
+    """Sizes 5 .. 13 run in the register sliding-sum kernel (one word per cell in shared memory; the float std packs the
+    integer part and the fraction into it when every fraction is exactly representable): same bits as the fused
+    prefix-sum kernel, on float and integer-valued DEMs, positive and negative elevations; a DEM with elevations near 0
+    is not eligible for the packed word and must still give the right answer."""
+    from topo_descriptors_b200 import _lib
+
+    def run(dem):
+        d = DeviceDEM(dev.to_device(dem))
+        return {s: (dev.tpi(d, s).cpu().numpy(), dev.std(d, s).cpu().numpy()) for s in (5, 7, 9, 11, 13)}
+
+    z = fractal_dem(700, 900, seed=31)
+    cases = {"float": z, "integer": np.rint(z).astype(np.float32), "negative": (-z).astype(np.float32),
+             "near zero": fractal_dem(500, 640, seed=32, zmin=0.0, zmax=500.0)}
+    for name, dem in cases.items():
+        got = run(dem)
+        _lib.set_option("tiny", False)
+        try:
+            want = run(dem)
+        finally:
+            _lib.set_option("tiny", True)
+        for s in got:
+            assert np.array_equal(got[s][0], want[s][0]), (name, "tpi", s)
+            assert np.array_equal(got[s][1], want[s][1]), (name, "std", s)
+        assert maxdiff(got[9][1], O.std_exact(dem, 9)) <= TOL_M, name
+        assert maxdiff(got[13][0], O.tpi_exact(dem, 13)) <= TOL_M, name

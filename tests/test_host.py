@@ -390,6 +390,12 @@ def test_disc_queries_agree_with_the_plan_over_a_size_x_range_grid():
     # FFT route: exactness of the rounded sums decides the split (an 0..8848 m range at size 801), not the 32-bit spans
     assert lib.topo_disc_plan_info(vp, 801, 1, 1, 200.0, 3400.0, 0, 0, info) == 0 and (info[17], info[16]) == (1, 0)
     assert lib.topo_disc_plan_info(vp, 801, 1, 1, 0.0, 8848.0, 0, 0, info) == 0 and (info[17], info[16]) == (1, 1)
+    # float std of sizes 5 .. 13: the packed-word register kernel when every fraction is exactly representable in the
+    # fraction field (|z| >= 2^(23 - Sf)), else the fused kernel; sizes above 13 stay fused
+    for (zmin, zmax, size, tiny) in ((200.0, 3400.0, 9, 1), (-3400.0, -200.0, 13, 1), (0.0, 500.0, 9, 0), (-50.0, 900.0, 5, 0),
+                                     (200.0, 3400.0, 15, 0), (200.0, 3400.0, 8, 0)):
+        assert lib.topo_disc_plan_info(vp, size, 1, 0, zmin, zmax, 0, 0, info) == 0 and (info[0], info[1], info[3]) == (3, 1, tiny), (
+            zmin, zmax, size, list(info)[:4])
 
 
 def test_tiler_band_plan_and_stats_merge():

@@ -121,6 +121,7 @@ struct DiscParams {
     long long n_ll;
     double nc0_scaled, n_tmin;  // N*c0 (TPI_Q: times 2^-S folded in) and N*tmin as doubles, for the 32-bit epilogue
     double inv_n_nm1;  // 1 / (N * (N - 1))
+    int fpack;         // tiny float std: bits of the fraction field of the packed word
     int qsplit;        // STD: the square plane is split in PL_QL + PL_QH (raw sums of PL_QH: partial plane NARR)
     int exact64;       // N*B - a^2 fits in 64-bit integers
     int excl;          // TPI: offset (excl, excl) of the excluded "mid point" (0 odd size, -1 even size)
@@ -505,16 +506,19 @@ struct TinyWidths {
 
 template <int MODE>
 struct TinyTraits;
+// LP: planes kept in shared memory; NS: sums kept per output pixel; SQ: the square plane is derived from plane 0.
+// PACK (float std): ONE word per cell, (t - tmin) << fpack | fraction -- a second plane would leave a single CTA per SM.
+// The sums kept are T, Q and W = sum of the packed words (mod 2^32): the fraction sum is W - (T << fpack).
 template <>
-struct TinyTraits<TPI_I> { static constexpr int LP = 1; static constexpr bool SQ = false; };
+struct TinyTraits<TPI_I> { static constexpr int LP = 1, NS = 1; static constexpr bool SQ = false, PACK = false; };
 template <>
-struct TinyTraits<TPI_Q> { static constexpr int LP = 1; static constexpr bool SQ = false; };
+struct TinyTraits<TPI_Q> { static constexpr int LP = 1, NS = 1; static constexpr bool SQ = false, PACK = false; };
 template <>
-struct TinyTraits<TPI_X> { static constexpr int LP = 2; static constexpr bool SQ = false; };
+struct TinyTraits<TPI_X> { static constexpr int LP = 2, NS = 2; static constexpr bool SQ = false, PACK = false; };
 template <>
-struct TinyTraits<STD_I> { static constexpr int LP = 1; static constexpr bool SQ = true; };
+struct TinyTraits<STD_I> { static constexpr int LP = 1, NS = 2; static constexpr bool SQ = true, PACK = false; };
 template <>
-struct TinyTraits<STD_F> { static constexpr int LP = 2; static constexpr bool SQ = true; };
+struct TinyTraits<STD_F> { static constexpr int LP = 1, NS = 3; static constexpr bool SQ = true, PACK = true; };
 
 // the planes a tiny kernel LOADS (the square plane of STD is derived from plane 0)
 template <int MODE>
@@ -524,7 +528,10 @@ __device__ __forceinline__ void convert_tiny(const DiscParams& p, float z, uint3
     } else {
         const int t = __float2int_rz(z);
         v[0] = (uint32_t)(t - p.tmin);
-        if constexpr (TinyTraits<MODE>::LP == 2) v[1] = (uint32_t)__float2int_rn(((z - (float)t) + 1.0f) * p.fscale);
+        if constexpr (TinyTraits<MODE>::PACK)
+            v[0] = (v[0] << p.fpack) | (uint32_t)__float2int_rn(((z - (float)t) + 1.0f) * p.fscale);
+        else if constexpr (TinyTraits<MODE>::LP == 2)
+            v[1] = (uint32_t)__float2int_rn(((z - (float)t) + 1.0f) * p.fscale);
     }
 }
 
@@ -532,9 +539,9 @@ template <int MODE, int M>
 __global__ void __launch_bounds__(256) disc_tiny_kernel(const DiscParams p) {
     constexpr int D = 2 * M + 1;
     constexpr int LP = TinyTraits<MODE>::LP;
-    constexpr bool SQ = TinyTraits<MODE>::SQ;
-    constexpr int NS = LP + (SQ ? 1 : 0);          // sums kept per output pixel
-    constexpr int NARR = ModeTraits<MODE>::NARR;   // == NS, in the order (T, Q, F) / (T, F) / (q)
+    constexpr bool SQ = TinyTraits<MODE>::SQ, PACK = TinyTraits<MODE>::PACK;
+    constexpr int NS = TinyTraits<MODE>::NS;       // sums kept per output pixel
+    constexpr int NARR = ModeTraits<MODE>::NARR;   // == NS, in the order (T, Q, F | W) / (T, F) / (q)
     static_assert(NS == NARR, "plane bookkeeping");
     constexpr int TC = kTinyTile + 2 * M;          // tile columns
     constexpr int PITCH = TC + 1;
@@ -614,6 +621,21 @@ __global__ void __launch_bounds__(256) disc_tiny_kernel(const DiscParams p) {
             // widening: R[w] = R[w-1] + q[-w] + q[+w]
 #pragma unroll
             for (int w = 0; w <= M; ++w) {
+                if constexpr (PACK) {
+                    const int fb = p.fpack;
+                    if (w == 0) {
+                        const uint32_t c0 = row[0], t0 = c0 >> fb;
+                        const int d0 = (int)t0 - dq;
+                        R[0][0] = t0, R[0][1] = (uint32_t)(d0 * d0), R[0][2] = c0;
+                    } else {
+                        const uint32_t l = row[-w], r = row[w], tl = l >> fb, tr = r >> fb;
+                        const int dl = (int)tl - dq, dr = (int)tr - dq;
+                        R[w][0] = R[w - 1][0] + tl + tr;
+                        R[w][1] = R[w - 1][1] + (uint32_t)(dl * dl) + (uint32_t)(dr * dr);
+                        R[w][2] = R[w - 1][2] + l + r;
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int a = 0; a < LP; ++a) {
                     const uint32_t* pl = row + a * TR * PITCH;
@@ -670,6 +692,7 @@ __global__ void __launch_bounds__(256) disc_tiny_kernel(const DiscParams p) {
                             unsigned long long a64[NARR];
 #pragma unroll
                             for (int a = 0; a < NS; ++a) a64[a] = acc[slot][a];
+                            if constexpr (PACK) a64[2] = (uint32_t)(acc[slot][2] - (acc[slot][0] << p.fpack));  // the fraction sum
                             res = finish<MODE>(p, a64, gy, x);
                         }
                         p.out[(int64_t)(gy - p.out_gy0) * p.ld_out + x] = res;
@@ -1790,6 +1813,25 @@ static int plan_disc_impl(const topo_view* v, int size, int what, int all_intege
         // (one loaded plane only: with two the 128 x 128 tile leaves a single CTA per SM and the prefix kernel wins)
         pl.tiny = (size & 1) && size >= 5 && size <= 13 && acc == full && (mode == TPI_I || mode == TPI_Q || mode == STD_I) &&
                   option_enabled(kOptTiny);
+        if (mode == STD_F && (size & 1) && size >= 5 && size <= 13 && !qsplit && option_enabled(kOptTiny)) {
+            // float std: integer part and fraction packed in one word, (t - tmin) << fpack | (frac + 1) * 2^Sf with
+            // fpack = Sf + 2.  Exact -- and then bit-identical to the fused kernel's 2^23 fraction plane -- when every
+            // float32 fraction has at most Sf bits, i.e. |z| >= 2^(23 - Sf) (or z = 0, the padding); the three sums of
+            // a disc of N <= 137 cells must fit 32 bits.
+            const int tb = ilog2_floor(trange + 1.0) + 1;
+            int Sf = 30 - tb;
+            if (Sf > 23) Sf = 23;
+            const double zlow = ldexp(1.0, 23 - Sf);
+            const double half = floor(trange / 2.0) + 1.0;
+            if (Sf >= 12 && (zmin >= zlow || zmax <= -zlow) && n * ldexp(2.0, Sf) < kU32 && n * half * half < kU32 &&
+                n * (trange + 1.0) < kU32) {
+                pl.tiny = true;
+                p.fpack = Sf + 2;
+                p.fscale = (float)ldexp(1.0, Sf);
+                p.inv_fscale = ldexp(1.0, -Sf);
+                acc = full;
+            }
+        }
         if (acc != full) acc &= 1;
     }
     pl.acc = acc;
