@@ -624,9 +624,15 @@ def run_gpu(args, rank, world, local_rank):
     tile_V = tile_T - 2 * tile_H
     spec = (-(-ctx.rows // tile_V)) * (-(-nx // tile_V)) * tile_T * tile_T * 16.0 / band_px
     keep = tile_V / tile_T  # share of a first-pass line the second pass needs (the rest is neither stored nor transposed)
-    moved = {"disc_fft_inv": (1 + keep) * spec, "disc_fft_store": keep * spec + 16, "disc_fft_planes": 4 + spec,
-             "disc_fft_finish<TPI_X>": keep * spec + 4, "disc_fft_finish<STD_F>": keep * spec + 20,
-             "disc_fft_finish<TPI_I>": keep * spec + 4, "disc_fft_finish<STD_I>": keep * spec + 12,
+    # a plane that travels alone is laid out as twin tiles: those transforms move half the planes
+    n_inv = max(1, kernels.get("disc_fft_inv", {}).get("launches", 1))
+    n_twin = sum(v["launches"] for k, v in kernels.items() if k.startswith("disc_fft_finish") and ",twin>" in k)
+    mix = (n_inv - 0.5 * min(n_twin, n_inv)) / n_inv
+    moved = {"disc_fft_inv": (1 + keep) * spec * mix, "disc_fft_store": keep * spec + 16, "disc_fft_planes": 4 + spec * (0.75 if n_twin else 1.0),
+             "disc_fft_finish<STD_F,twin>": keep * spec / 2 + 20, "disc_fft_finish<STD_I,twin>": keep * spec / 2 + 12,
+             # (tpi of a tpi + std pair also leaves its two plane sums for the std: 16 B/px)
+             "disc_fft_finish<TPI_X>": keep * spec + 20, "disc_fft_finish<STD_F>": keep * spec + 20,
+             "disc_fft_finish<TPI_I>": keep * spec + 20, "disc_fft_finish<STD_I>": keep * spec + 12,
              "disc_finish<STD_F>": 28, "disc_finish<TPI_X>": 24, "disc_finish<STD_I>": 20, "disc_finish<TPI_I>": 16,
              "gauss_fft": 8, "transpose": 8}
     memory_bound = {}

@@ -55,6 +55,8 @@ typedef struct topo_disc_cache {
     int valid;    /* in/out: bits 2k / 2k+1 = row prefix / column-side tables of plane kind k
                      (0 trunc(z) - tmin, 1 its square (or the low 16 bits of a split square), 2 fraction,
                      3 quantised elevation; the high half of a split square takes the next free kind) */
+    int mask_size; /* in/out, FFT route: the disc size whose mask spectrum sits behind the plane spectra (tpi(size) and
+                      std(size) of a pair build it once); start with 0 */
 } topo_disc_cache;
 
 /* ---- library ------------------------------------------------------------------------------ */

@@ -11,8 +11,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-fi
     python bench.py --steps 2 --warmup 1 --no-cpu --no-extra > $O/r02b_ncu_launches.log 2>&1
 # full-set captures, one call per descriptor class in sweep mode on an 8192^2 float DEM (plane spectra cached, FFT disc
 # route, FFT Gaussian, fused gradient, fused / tiny small discs), condensed to CSV
-PROF_SIZE=8192 PROF_FLOAT=1 PROF_SHARE=801 ncu --set full --clock-control none -c 90 -f -o /tmp/r02b_prof \
-    python profiles/prof_driver.py tpi:801 std:801 tpi:401 std:401 grad:801 grad:161 tpi:21 std:21 tpi:5 std:5 grad:5 grad:21 sobel:0 > $O/r02b_prof.log 2>&1
+PROF_SIZE=8192 PROF_FLOAT=1 PROF_SHARE=801 ncu --set full --clock-control none -c 110 -f -o /tmp/r02b_prof \
+    python profiles/prof_driver.py tpi:801 std:801 tpi:401 std:401 grad:801 grad:161 grad:5 grad:21 sobel:0 tpi:21 std:21 tpi:5 std:5 std:13 > $O/r02b_prof.log 2>&1
 python profiles/ncu_summary.py /tmp/r02b_prof.ncu-rep > $O/r02b_ncu_full_summary.csv
 # valley/ridge FFT route (size 41, 2048^2)
 PROF_SIZE=2048 ncu --set full --clock-control none -k regex:"vfft|rotate|fft2d" -c 14 -f -o /tmp/r02b_prof_valley \

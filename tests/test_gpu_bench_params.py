@@ -47,6 +47,7 @@ def test_tpi_std_401_801_inside_a_cached_sweep(terrain, kind):
         assert maxdiff(dev.tpi(shared, s, pair_std=True).cpu().numpy(), want[s][0]) <= TOL_M, (kind, s)
         assert maxdiff(dev.std(shared, s).cpu().numpy(), want[s][1]) <= TOL_M, (kind, s)
     assert shared._plane_cache is not None and shared._plane_cache[1].valid != 0
+    assert shared._plane_cache[1].mask_size == 801  # the mask spectrum tpi(801) built, reused by std(801)
     shared.release_disc_planes()
     assert maxdiff(topo.tpi(z, 801), want[801][0]) <= TOL_M
     assert maxdiff(topo.std(z, 401), want[401][1]) <= TOL_M

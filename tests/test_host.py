@@ -290,8 +290,9 @@ def test_library_exports_every_declared_symbol():
     # with a plane cache the planes live there: the workspace shrinks and mid sizes walk the cached planes
     rng = (200.0, 3400.0)
     # FFT route (default for sizes >= 128): the cache holds one plane spectrum per plane pair (T = 4096, one tile)
-    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) == 4096 * 4096 * 16
-    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0, *rng) == 2 * 4096 * 4096 * 16
+    # (plane spectra: one pair for integer-valued DEMs, two for float ones, + the mask spectrum of the size in flight)
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) == 2 * 4096 * 4096 * 16
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0, *rng) == 3 * 4096 * 4096 * 16
     assert lib.topo_disc_shares_tsum(ctypes.byref(v), 401, 1, *rng, 801) == 2  # T and the square plane ride together
     _lib.set_option("disc_fft", False)  # the prefix-plane walk and its plane cache
     assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) > 10 * 4 * 900 * 1440

@@ -35,7 +35,7 @@ _VP = POINTER(View)
 class DiscCache(ctypes.Structure):
     """``topo_disc_cache`` (include/topo_b200.h): prefix planes shared by tpi / std calls at several sizes."""
 
-    _fields_ = [("mem", c_void_p), ("bytes", c_size_t), ("max_size", c_int), ("valid", c_int)]
+    _fields_ = [("mem", c_void_p), ("bytes", c_size_t), ("max_size", c_int), ("valid", c_int), ("mask_size", c_int)]
 
 
 _CP = POINTER(DiscCache)

@@ -2079,6 +2079,15 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
     double2* Y = reinterpret_cast<double2*>(ws + pl.off_y);
     double2* K1 = reinterpret_cast<double2*>(ws + pl.off_k1);
     double2* K2 = reinterpret_cast<double2*>(ws + pl.off_k2);
+    const size_t spectra_bytes = (size_t)pl.fft_pairs * pl.fft_plane_bytes;
+    bool have_mask = false;
+    if (cache) {
+        // the mask spectrum lives behind the plane spectra: tpi(size) and std(size) of a pair build it once
+        TOPO_CHECK(cache->bytes >= spectra_bytes + (size_t)N * N * sizeof(double2), "plane cache too small: need %zu bytes, got %zu",
+                   spectra_bytes + (size_t)N * N * sizeof(double2), cache->bytes);
+        K1 = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(cache->mem) + spectra_bytes);
+        have_mask = cache->mask_size == p.k;
+    }
     const int tiles = g.tiles_y * g.tiles_x;
     TOPO_CHECK(tiles <= 65535, "too many tiles for one launch: split the DEM in row bands");
     const dim3 kgrid(N / 32, N / 32, 1);
@@ -2118,10 +2127,14 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
     }
     if (njobs > 0) {
         TOPO_LAUNCH("disc_fft_twiddles", s, fft_twiddle_kernel<<<ceil_div(N, 256), 256, 0, s>>>(tw, N));
-        // spectrum of the disc mask (its lines stored by eights: the order the product pass reads them in)
-        TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(p, g, K1, tw)));
-        TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
-        TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N, true><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
+        if (!have_mask) {
+            // spectrum of the disc mask (its lines stored by eights: the order the product pass reads them in)
+            if (cache) cache->mask_size = 0;
+            TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(p, g, K1, tw)));
+            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
+            TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N, true><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
+            if (cache) cache->mask_size = p.k;
+        }
     }
     const double scale = 1.0 / ((double)N * (double)N);
     for (int j = 0; j < njobs; ++j) {
@@ -2312,7 +2325,8 @@ int topo_disc_shares_tsum(const topo_view* v, int size, int all_integer, double 
 size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer, double zmin, double zmax) {
     DiscPlan pl;
     if (!quiet_plan(v, max_size, 1, all_integer, zmin, zmax, max_size, pl)) return 0;
-    if (pl.fft) return pl.cached ? (size_t)pl.fft_pairs * pl.fft_plane_bytes : 0;  // plane spectra, one per pair
+    // plane spectra, one per pair, + the mask spectrum of the size in flight
+    if (pl.fft) return pl.cached ? (size_t)pl.fft_pairs * pl.fft_plane_bytes + (size_t)pl.fg.T * pl.fg.T * sizeof(double2) : 0;
     if (pl.fused || !pl.cached) return 0;
     // integer-valued DEMs use two plane kinds (trunc(z) - tmin, its square); float DEMs add the fraction and the
     // quantised-elevation planes; a split square adds its high half
