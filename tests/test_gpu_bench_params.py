@@ -379,7 +379,11 @@ def test_disc_fft_route_is_bit_identical_to_the_prefix_plane_walk():
     zwt = fractal_dem(1100, 4100, seed=29, zmin=0.0, zmax=8848.0, integer=True)
     cases = [(zi, [129, 200, 401], None, False), (z, [161, 301], None, True), (zi, [41, 161, 401, 801], 801, True),
              (z, [81, 241, 801], 801, True), (zw, [401], None, False), (zt, [129, 161], None, True), (zo, [135, 65], 135, True),
-             (zwt, [201], None, False)]
+             (zwt, [201], None, False),
+             # window rows: 1300 + 2 x 400 fit ONE 3072-point transform along y (cases above); 4000 rows take two of them
+             # (6144 window rows) rather than two of 4096; float DEM: twin tiles on the rectangular windows
+             (np.rint(fractal_dem(4000, 1100, seed=30)).astype(np.float32), [801], None, False),
+             (fractal_dem(3500, 900, seed=33), [601], None, True)]
     for dem, sizes, hint, pair in cases:
         got = run(dem, sizes, hint, pair)
         _lib.set_option("disc_fft", False)

@@ -289,10 +289,15 @@ def test_library_exports_every_declared_symbol():
     assert lib.topo_disc_workspace_bytes(ctypes.byref(v), 801, 0, 1, 200.0, 3400.0, 0, 0) > 4 * 900 * 1440
     # with a plane cache the planes live there: the workspace shrinks and mid sizes walk the cached planes
     rng = (200.0, 3400.0)
-    # FFT route (default for sizes >= 128): the cache holds one plane spectrum per plane pair (T = 4096, one tile)
-    # (plane spectra: one pair for integer-valued DEMs, two for float ones, + the mask spectrum of the size in flight)
-    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) == 2 * 4096 * 4096 * 16
-    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0, *rng) == 3 * 4096 * 4096 * 16
+    # FFT route (default for sizes >= 128): the cache holds one plane spectrum per plane pair (one tile: 4096 columns x
+    # 3072 rows -- 900 rows + 2 x 400 of halo fit the shorter transform along y) + the mask spectrum of the size in flight
+    # (plane spectra: one pair for integer-valued DEMs, two for float ones)
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) == 2 * 4096 * 3072 * 16
+    assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 0, *rng) == 3 * 4096 * 3072 * 16
+    tall = _lib.View(1440, 16384, 0, 16384, 0, 16384)  # a whole 16384-row image: five 4096-row windows beat eight of 3072
+    assert lib.topo_disc_cache_bytes(ctypes.byref(tall), 801, 1, *rng) == (5 + 1) * 4096 * 4096 * 16
+    band = _lib.View(1440, 16384, 1648, 2848, 2048, 2048)  # a 2048-row band of it (8 GPUs): one 3072-row window
+    assert lib.topo_disc_cache_bytes(ctypes.byref(band), 801, 1, *rng) == 2 * 4096 * 3072 * 16
     assert lib.topo_disc_shares_tsum(ctypes.byref(v), 401, 1, *rng, 801) == 2  # T and the square plane ride together
     _lib.set_option("disc_fft", False)  # the prefix-plane walk and its plane cache
     assert lib.topo_disc_cache_bytes(ctypes.byref(v), 801, 1, *rng) > 10 * 4 * 900 * 1440

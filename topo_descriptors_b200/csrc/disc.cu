@@ -1266,7 +1266,8 @@ __global__ void __launch_bounds__(256) disc_finish_kernel(const DiscParams p) {
 // planes ride in the real and imaginary parts), independent of the size: 8.3 ms per pair at 16384^2 against 29-34 ms
 // per plane for the size-801 walk.  The forward transforms of the planes are shared by all sizes of a sweep (cache).
 struct DfftGeom {
-    int T, H, V, tiles_y, tiles_x;  // transform length, window halo, outputs per tile edge
+    int T, H, V, tiles_y, tiles_x;  // transform length along x, window halo, outputs per tile along x
+    int Ty, Vy;                     // transform length / outputs per tile along y (a thin band takes a shorter transform)
 };
 
 __device__ __forceinline__ double plane_value_rt(const DiscParams& p, int mode, float z) {
@@ -1312,7 +1313,7 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     int c0_a, c0_b = 0;
     auto locate = [&](int tile, const float*& row, bool& ok, int& c0) {
         const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-        const int gy = p.out_gy0 + ty * g.V - g.H + line;
+        const int gy = p.out_gy0 + ty * g.Vy - g.H + line;
         c0 = tx * g.V - g.H;
         ok = gy >= 0 && gy < p.gny && gy >= p.in_gy0 && gy < p.in_gy0 + p.in_rows;
         row = p.dem + (int64_t)(ok ? gy - p.in_gy0 : 0) * p.ld_in;
@@ -1331,7 +1332,7 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
             im = plane_value_rt(p, mode_b, z);
         }
         return make_double2(plane_value_rt(p, mode_a, z), im);
-    }, dst + ((int64_t)plane * N + line) * N);
+    }, dst + ((int64_t)plane * gridDim.x + line) * N);  // (grid: Ty lines x planes)
 }
 
 // first forward pass of the disc mask (circular_kernel / the square of sizes < 5), placed so that scipy's "same" crop
@@ -1373,8 +1374,8 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     // output row / first column / column bound of a tile for this window line (row < 0: nothing to produce)
     auto locate = [&](int tile, int& gy, int& ox0, int& x_hi) {
         const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
-        const int oy0 = p.out_gy0 + ty * g.V;
-        const int oy1 = min(oy0 + g.V, p.out_gy0 + p.out_rows);
+        const int oy0 = p.out_gy0 + ty * g.Vy;
+        const int oy1 = min(oy0 + g.Vy, p.out_gy0 + p.out_rows);
         gy = oy0 + line - 2 * g.H;
         if (tile >= g.tiles_y * g.tiles_x || gy < oy0 || gy >= oy1) gy = -1;
         ox0 = tx * g.V;
@@ -1384,7 +1385,7 @@ __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     locate(TWIN ? 2 * plane : plane, gy_a, ox_a, xh_a);
     if constexpr (TWIN) locate(2 * plane + 1, gy_b, ox_b, xh_b);
     if (gy_a < 0 && gy_b < 0) return;  // CTA-uniform
-    const double2* __restrict__ in = src + ((int64_t)plane * N + line) * N;
+    const double2* __restrict__ in = src + ((int64_t)plane * gridDim.x + line) * N;  // (grid: Ty lines x planes)
     if constexpr (FIN >= 0) {
         // The epilogue reads, per pixel, the sums another pass left in HBM (and the DEM for TPI) right after the last
         // butterfly stage, one dependent load per output: fetch those rows into L2 now, while the transform runs.
@@ -1673,13 +1674,20 @@ static void plan_fft_geometry(const topo_view* v, int size, int narr, int plane_
     g.H = plane_halo > 0 ? plane_halo : size / 2;
     g.T = dfft_length(g.H);
     g.V = g.T - 2 * g.H;
-    g.tiles_y = ceil_div(v->out_rows, g.V), g.tiles_x = ceil_div(v->nx, g.V);
+    // along y a 4096-row window may be more than a thin row band needs (2048 rows + 2 x 400 of halo on 8 GPUs): a
+    // 3072-point transform (radix-6 leading stage) is taken when it covers the rows with fewer window rows in total
+    g.Ty = g.T;
+    if (g.T == 4096 && 3072 - 2 * g.H > 0 &&
+        (long long)ceil_div(v->out_rows, 3072 - 2 * g.H) * 3072 < (long long)ceil_div(v->out_rows, g.V) * 4096)
+        g.Ty = 3072;
+    g.Vy = g.Ty - 2 * g.H;
+    g.tiles_y = ceil_div(v->out_rows, g.Vy), g.tiles_x = ceil_div(v->nx, g.V);
     pl.fft_pairs = pairs;
-    pl.fft_plane_bytes = (size_t)g.tiles_y * g.tiles_x * g.T * g.T * sizeof(double2);
+    pl.fft_plane_bytes = (size_t)g.tiles_y * g.tiles_x * g.T * g.Ty * sizeof(double2);
     auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t one = (size_t)g.T * g.T * sizeof(double2);
+    const size_t one = (size_t)g.T * g.Ty * sizeof(double2);
     size_t off = 0;
-    pl.off_tw = off, off = align(off + (size_t)g.T * sizeof(double2));
+    pl.off_tw = off, off = align(off + (size_t)(g.T + g.Ty) * sizeof(double2));  // twiddles of both lengths
     pl.off_dhat = off;
     if (!pl.cached) off = align(off + pairs * pl.fft_plane_bytes);  // with a cache the plane spectra live there
     pl.off_x = off, off = align(off + pl.fft_plane_bytes);
@@ -2053,44 +2061,47 @@ static int launch_two_pass(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo
 }
 
 // ---- FFT route: launches ------------------------------------------------------------------------------------------
-template <int N>
+// NX / NY: transform lengths along x (lines = window rows) and along y (lines = window columns)
+template <int NX, int NY>
 static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo_disc_cache* cache, unsigned char* ws) {
-    using S = FftShape<N>;
+    using SX = FftShape<NX>;
+    using SY = FftShape<NY>;
     const DiscParams& p = pl.p;
     const DfftGeom& g = pl.fg;
     static bool attr_set[64] = {false};
     int dev = 0;
     TOPO_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_planes_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_disc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, -1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, TPI_I, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, TPI_X, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_I, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_I, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<N, STD_F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-        if (fft2d_set_smem_attributes<N>()) return -2;
+        TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_planes_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SX::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute(dfft_fwd_disc_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SX::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<NX, -1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SX::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<NX, TPI_I, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SX::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<NX, TPI_X, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SX::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<NX, STD_I, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SX::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<NX, STD_F, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SX::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<NX, STD_I, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SX::SMEM));
+        TOPO_CUDA(cudaFuncSetAttribute((dfft_store_kernel<NX, STD_F, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SX::SMEM));
+        if (fft2d_set_smem_attributes<NY>()) return -2;
         if (dev < 64) attr_set[dev] = true;
     }
-    double2* tw = reinterpret_cast<double2*>(ws + pl.off_tw);
+    double2* twx = reinterpret_cast<double2*>(ws + pl.off_tw);
+    double2* twy = NX == NY ? twx : twx + NX;
     double2* X = reinterpret_cast<double2*>(ws + pl.off_x);
     double2* Y = reinterpret_cast<double2*>(ws + pl.off_y);
     double2* K1 = reinterpret_cast<double2*>(ws + pl.off_k1);
     double2* K2 = reinterpret_cast<double2*>(ws + pl.off_k2);
     const size_t spectra_bytes = (size_t)pl.fft_pairs * pl.fft_plane_bytes;
+    const size_t mask_bytes = (size_t)NX * NY * sizeof(double2);
     bool have_mask = false;
     if (cache) {
         // the mask spectrum lives behind the plane spectra: tpi(size) and std(size) of a pair build it once
-        TOPO_CHECK(cache->bytes >= spectra_bytes + (size_t)N * N * sizeof(double2), "plane cache too small: need %zu bytes, got %zu",
-                   spectra_bytes + (size_t)N * N * sizeof(double2), cache->bytes);
+        TOPO_CHECK(cache->bytes >= spectra_bytes + mask_bytes, "plane cache too small: need %zu bytes, got %zu",
+                   spectra_bytes + mask_bytes, cache->bytes);
         K1 = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(cache->mem) + spectra_bytes);
         have_mask = cache->mask_size == p.k;
     }
     const int tiles = g.tiles_y * g.tiles_x;
     TOPO_CHECK(tiles <= 65535, "too many tiles for one launch: split the DEM in row bands");
-    const dim3 kgrid(N / 32, N / 32, 1);
     const bool reuse = tsum_op == 2;  // a previous call of the pair left the sums of plane pair 0 in tsum / qsum / fsum
     const int q_lo = p.qsplit ? PL_QL : PL_Q;
     unsigned long long* part = p.partial;
@@ -2125,18 +2136,20 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
             jobs[njobs++] = {1, q_lo, p.qsplit ? PL_QH : -1, nullptr, nullptr};
             break;
     }
+    // window planes are [NY rows][NX columns]; their spectra and the first inverse pass work on [NX lines][NY]
     if (njobs > 0) {
-        TOPO_LAUNCH("disc_fft_twiddles", s, fft_twiddle_kernel<<<ceil_div(N, 256), 256, 0, s>>>(tw, N));
+        TOPO_LAUNCH("disc_fft_twiddles", s, fft_twiddle_kernel<<<ceil_div(NX, 256), 256, 0, s>>>(twx, NX));
+        if (NX != NY) TOPO_LAUNCH("disc_fft_twiddles", s, fft_twiddle_kernel<<<ceil_div(NY, 256), 256, 0, s>>>(twy, NY));
         if (!have_mask) {
             // spectrum of the disc mask (its lines stored by eights: the order the product pass reads them in)
             if (cache) cache->mask_size = 0;
-            TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<N><<<dim3(N, 1), S::NT, S::SMEM, s>>>(p, g, K1, tw)));
-            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
-            TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N, true><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
+            TOPO_LAUNCH("disc_fft_mask", s, (dfft_fwd_disc_kernel<NX><<<dim3(NY, 1), SX::NT, SX::SMEM, s>>>(p, g, K1, twx)));
+            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<dim3(NX / 32, NY / 32, 1), dim3(32, 8), 0, s>>>(K1, K2, NY, NX));
+            TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<NY, true><<<dim3(NX, 1), SY::NT, SY::SMEM, s>>>(K2, K1, twy)));
             if (cache) cache->mask_size = p.k;
         }
     }
-    const double scale = 1.0 / ((double)N * (double)N);
+    const double scale = 1.0 / ((double)NX * (double)NY);
     for (int j = 0; j < njobs; ++j) {
         const Job& job = jobs[j];
         const bool twin = job.pair == 1 && job.mb < 0;
@@ -2144,26 +2157,24 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
         double2* dhat;
         bool have = false;
         if (cache) {
-            TOPO_CHECK(cache->bytes >= (size_t)pl.fft_pairs * pl.fft_plane_bytes, "plane cache too small: need %zu bytes, got %zu",
-                       (size_t)pl.fft_pairs * pl.fft_plane_bytes, cache->bytes);
             dhat = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(cache->mem) + (size_t)job.pair * pl.fft_plane_bytes);
             have = (cache->valid >> (16 + job.pair)) & 1;
         } else {
             dhat = reinterpret_cast<double2*>(ws + pl.off_dhat + (size_t)job.pair * pl.fft_plane_bytes);
         }
         if (!have) {
-            TOPO_LAUNCH("disc_fft_planes", s, (dfft_fwd_planes_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(p, g, job.ma, job.mb, twin ? 1 : 0, X, tw)));
-            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<dim3(N / 32, N / 32, planes), dim3(32, 8), 0, s>>>(X, Y, N));
-            TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(Y, dhat, tw)));
+            TOPO_LAUNCH("disc_fft_planes", s, (dfft_fwd_planes_kernel<NX><<<dim3(NY, planes), SX::NT, SX::SMEM, s>>>(p, g, job.ma, job.mb, twin ? 1 : 0, X, twx)));
+            TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<dim3(NX / 32, NY / 32, planes), dim3(32, 8), 0, s>>>(X, Y, NY, NX));
+            TOPO_LAUNCH("disc_fft_fwd", s, (fft2d_fwd_cplx_kernel<NY><<<dim3(NX, planes), SY::NT, SY::SMEM, s>>>(Y, dhat, twy)));
             if (cache) cache->valid |= 1 << (16 + job.pair);
         }
         // only the window rows the store pass turns into pixels travel through the first pass's stores and the transpose
-        const int ct0 = (2 * g.H) / 32, ct1 = ceil_div(2 * g.H + g.V, 32);
-        TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(planes, N), S::NT, S::SMEM, s>>>(dhat, K1, X, tw, ct0 * 32, ct1 * 32)));
-        TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<dim3(ct1 - ct0, N / 32, planes), dim3(32, 8), 0, s>>>(X, Y, N, ct0));
-        const dim3 sgrid(N, planes);
+        const int ct0 = (2 * g.H) / 32, ct1 = ceil_div(2 * g.H + g.Vy, 32);
+        TOPO_LAUNCH("disc_fft_inv", s, (fft2d_inv_product_kernel<NY><<<dim3(planes, NX), SY::NT, SY::SMEM, s>>>(dhat, K1, X, twy, ct0 * 32, ct1 * 32)));
+        TOPO_LAUNCH("disc_fft_transpose", s, fft2d_transpose_kernel<<<dim3(ct1 - ct0, NX / 32, planes), dim3(32, 8), 0, s>>>(X, Y, NX, NY, ct0));
+        const dim3 sgrid(NY, planes);
 #define TOPO_DFFT_STORE(LABEL, FIN, TWIN) \
-    TOPO_LAUNCH(LABEL, s, (dfft_store_kernel<N, FIN, TWIN><<<sgrid, S::NT, S::SMEM, s>>>(p, g, Y, tw, job.da, job.db, job.ma, job.mb, scale)))
+    TOPO_LAUNCH(LABEL, s, (dfft_store_kernel<NX, FIN, TWIN><<<sgrid, SX::NT, SX::SMEM, s>>>(p, g, Y, twx, job.da, job.db, job.ma, job.mb, scale)))
         if (j + 1 < njobs) {
             TOPO_CHECK(!twin, "internal: a twin-tile job must be the last one of its descriptor");
             TOPO_DFFT_STORE("disc_fft_store", -1, false);
@@ -2197,9 +2208,11 @@ static int launch_fft_route_n(const DiscPlan& pl, int tsum_op, cudaStream_t s, t
 
 static int launch_fft_route(const DiscPlan& pl, int tsum_op, cudaStream_t s, topo_disc_cache* cache, unsigned char* ws) {
     switch (pl.fg.T) {
-        case 2048: return launch_fft_route_n<2048>(pl, tsum_op, s, cache, ws);
-        case 4096: return launch_fft_route_n<4096>(pl, tsum_op, s, cache, ws);
-        default: return launch_fft_route_n<8192>(pl, tsum_op, s, cache, ws);
+        case 2048: return launch_fft_route_n<2048, 2048>(pl, tsum_op, s, cache, ws);
+        case 4096:
+            return pl.fg.Ty == 3072 ? launch_fft_route_n<4096, 3072>(pl, tsum_op, s, cache, ws)
+                                    : launch_fft_route_n<4096, 4096>(pl, tsum_op, s, cache, ws);
+        default: return launch_fft_route_n<8192, 8192>(pl, tsum_op, s, cache, ws);
     }
 }
 
@@ -2326,7 +2339,7 @@ size_t topo_disc_cache_bytes(const topo_view* v, int max_size, int all_integer, 
     DiscPlan pl;
     if (!quiet_plan(v, max_size, 1, all_integer, zmin, zmax, max_size, pl)) return 0;
     // plane spectra, one per pair, + the mask spectrum of the size in flight
-    if (pl.fft) return pl.cached ? (size_t)pl.fft_pairs * pl.fft_plane_bytes + (size_t)pl.fg.T * pl.fg.T * sizeof(double2) : 0;
+    if (pl.fft) return pl.cached ? (size_t)pl.fft_pairs * pl.fft_plane_bytes + (size_t)pl.fg.T * pl.fg.Ty * sizeof(double2) : 0;
     if (pl.fused || !pl.cached) return 0;
     // integer-valued DEMs use two plane kinds (trunc(z) - tmin, its square); float DEMs add the fraction and the
     // quantised-elevation planes; a split square adds its high half

@@ -114,19 +114,19 @@ __device__ __forceinline__ void fft2d_inverse_line_product(double2* buf, const d
     fft_inverse_outer<N>(buf, tw, tid, store_out);
 }
 
-// second forward pass (and the first one of complex data): [planes][N][N] natural order -> digit-reversed lines
+// second forward pass (and the first one of complex data): [planes][lines][N] natural order -> digit-reversed lines
 // (BY8: the lines of a multiplier spectrum, in the order fft2d_inverse_line_product reads them)
 template <int N, bool BY8 = false>
 static __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
     fft2d_fwd_cplx_kernel(const double2* __restrict__ src, double2* __restrict__ dst, const double2* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
-    const int64_t base = ((int64_t)blockIdx.y * N + blockIdx.x) * N;
+    const int64_t base = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * N;  // grid (lines, planes)
     fft2d_forward_line<N, BY8>(buf, tw, threadIdx.x, [&](int n) { return __ldg(src + base + n); }, dst + base);
 }
 
-// first inverse pass: the line is the product of two spectra (a: [planes][N][N], k: [N][N] with its lines stored by
-// eights, same for every plane);
+// first inverse pass: the line is the product of two spectra (a: [planes][lines][N], k: [lines][N] with its lines
+// stored by eights, same for every plane);
 // dst[plane][line][n] for n in [n_lo, n_hi) -- the columns the transpose pass will carry over (multiples of 32).
 // (Storing the lines already transposed -- 16-byte stores N x 16 bytes apart, one per row -- was measured: the first
 // pass grows from 3.2 to 6.3 ms per 25 tiles of 4096^2, more than the 2.2 ms transpose pass it would replace.)
@@ -136,26 +136,27 @@ static __global__ void __launch_bounds__(FftShape<N>::NT, N >= 8192 ? 1 : 3)
                              const double2* __restrict__ tw, int n_lo, int n_hi) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
-    // grid (planes, N): the planes of one line are neighbours in launch order, so the line of k they all multiply by is
-    // read from DRAM once and then served by L2 (with the planes outermost it came back from DRAM for every plane)
+    // grid (planes, lines): the planes of one line are neighbours in launch order, so the line of k they all multiply
+    // by is read from DRAM once and then served by L2 (with the planes outermost it came back from DRAM for every plane)
     const int plane = blockIdx.x, line = blockIdx.y;
-    const int64_t base = ((int64_t)plane * N + line) * N;
+    const int64_t base = ((int64_t)plane * gridDim.y + line) * N;
     double2* out = dst + base;
     fft2d_inverse_line_product<N>(buf, tw, threadIdx.x, a + base, k + (int64_t)line * N, [&](int n, double2 y) {
         if (n >= n_lo && n < n_hi) out[n] = y;
     });
 }
 
-// [planes][n][n] complex transpose, 32 x 32 tiles; blockIdx.x counts column tiles from col_tile0 (a caller that only
-// needs some rows of the result transposes only those columns of the source)
-static __global__ void __launch_bounds__(256) fft2d_transpose_kernel(const double2* __restrict__ in, double2* __restrict__ out, int n,
-                                                                     int col_tile0 = 0) {
+// [planes][rows][cols] -> [planes][cols][rows] complex transpose, 32 x 32 tiles (rows, cols multiples of 32): grid
+// (column tiles, row tiles, planes); blockIdx.x counts column tiles from col_tile0 (a caller that only needs some rows
+// of the result transposes only those columns of the source)
+static __global__ void __launch_bounds__(256) fft2d_transpose_kernel(const double2* __restrict__ in, double2* __restrict__ out, int rows,
+                                                                     int cols, int col_tile0 = 0) {
     __shared__ double2 t[32][33];
-    const int64_t base = (int64_t)blockIdx.z * n * n;
+    const int64_t base = (int64_t)blockIdx.z * rows * cols;
     const int c0 = (blockIdx.x + col_tile0) * 32, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) t[i][threadIdx.x] = __ldg(in + base + (int64_t)(r0 + i) * n + c0 + threadIdx.x);
+    for (int i = threadIdx.y; i < 32; i += 8) t[i][threadIdx.x] = __ldg(in + base + (int64_t)(r0 + i) * cols + c0 + threadIdx.x);
     __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) out[base + (int64_t)(c0 + i) * n + r0 + threadIdx.x] = t[threadIdx.x][i];
+    for (int i = threadIdx.y; i < 32; i += 8) out[base + (int64_t)(c0 + i) * rows + r0 + threadIdx.x] = t[threadIdx.x][i];
 }
 
 template <int N>

@@ -54,6 +54,35 @@ __device__ __forceinline__ void dft4(double2 (&v)[4]) {
     v[1] = cadd(a2, a3), v[3] = csub(a2, a3);
 }
 
+// 6-point DFT (two 3-point transforms + a radix-2 combination), natural order in and out.  INV: conjugate kernel.
+template <bool INV>
+__device__ __forceinline__ void dft3(double2 a, double2 b, double2 c, double2& x0, double2& x1, double2& x2) {
+    constexpr double h = 0.86602540378443864676;  // sqrt(3) / 2
+    const double2 s = cadd(b, c), d = csub(b, c);
+    x0 = cadd(a, s);
+    const double2 m = make_double2(a.x - 0.5 * s.x, a.y - 0.5 * s.y);
+    const double2 t = make_double2(h * d.x, h * d.y);
+    // forward: x1 = m - i t, x2 = m + i t; inverse: the other way round
+    const double2 p = make_double2(m.x + t.y, m.y - t.x), q = make_double2(m.x - t.y, m.y + t.x);
+    x1 = INV ? q : p;
+    x2 = INV ? p : q;
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft6(double2 (&v)[6]) {
+    constexpr double h = 0.86602540378443864676;
+    double2 e[3], o[3];
+    dft3<INV>(v[0], v[2], v[4], e[0], e[1], e[2]);
+    dft3<INV>(v[1], v[3], v[5], o[0], o[1], o[2]);
+    // w6^k o[k], w6 = exp(-+ i pi / 3) = (1/2, -+ sqrt(3)/2), w6^2 = (-1/2, -+ sqrt(3)/2)
+    const double sg = INV ? 1.0 : -1.0;
+    const double2 o1 = make_double2(0.5 * o[1].x - sg * h * o[1].y, 0.5 * o[1].y + sg * h * o[1].x);
+    const double2 o2 = make_double2(-0.5 * o[2].x - sg * h * o[2].y, -0.5 * o[2].y + sg * h * o[2].x);
+    v[0] = cadd(e[0], o[0]), v[3] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1), v[4] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2), v[5] = csub(e[2], o2);
+}
+
 __device__ __forceinline__ int pad(int i) { return i + (i >> 3); }
 
 // w^1 .. w^7 from ONE table entry: the stages are bound by shared-memory / L1 traffic (ncu: l1tex 92 %, FP64 pipe
@@ -71,7 +100,7 @@ __device__ __forceinline__ void twiddle_powers(double2 w1, double2 (&w)[8]) {
 
 template <int N>
 struct FftShape {
-    static constexpr int LEAD = (N == 8192 || N == 1024) ? 2 : (N == 2048 ? 4 : 1);  // N = LEAD * 8^k
+    static constexpr int LEAD = (N == 8192 || N == 1024) ? 2 : (N == 2048 ? 4 : (N == 3072 ? 6 : 1));  // N = LEAD * 8^k
     static constexpr int NT = N >= 8192 ? 512 : 256;                                  // threads per CTA
     static constexpr int M8 = N / LEAD;                                               // length the radix-8 stages start from
     static constexpr size_t SMEM = (size_t)(N + N / 8) * sizeof(double2);
@@ -102,6 +131,23 @@ __device__ __forceinline__ void fft_forward_outer(double2* buf, const double2* _
             buf[pad(j + St)] = cmul(v[1], w1);
             buf[pad(j + 2 * St)] = cmul(v[2], w2);
             buf[pad(j + 3 * St)] = cmul(v[3], w3);
+        }
+        __syncthreads();
+    }
+    else if constexpr (LEAD == 6) {
+        constexpr int St = N / 6;
+        for (int j = tid; j < St; j += NT) {
+            double2 v[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) v[q] = load_in(j + q * St);
+            dft6<false>(v);
+            buf[pad(j)] = v[0];
+            const double2 w1 = tw[j], w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2), w5 = cmul(w4, w1);
+            buf[pad(j + St)] = cmul(v[1], w1);
+            buf[pad(j + 2 * St)] = cmul(v[2], w2);
+            buf[pad(j + 3 * St)] = cmul(v[3], w3);
+            buf[pad(j + 4 * St)] = cmul(v[4], w4);
+            buf[pad(j + 5 * St)] = cmul(v[5], w5);
         }
         __syncthreads();
     }
@@ -187,6 +233,21 @@ __device__ __forceinline__ void fft_inverse_outer(double2* buf, const double2* _
             dft4<true>(v);
 #pragma unroll
             for (int q = 0; q < 4; ++q) store_out(j + q * St, v[q]);
+        }
+    } else if constexpr (LEAD == 6) {
+        constexpr int St = N / 6;
+        for (int j = tid; j < St; j += NT) {
+            double2 v[6];
+            v[0] = buf[pad(j)];
+            const double2 w1 = tw[j], w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2), w5 = cmul(w4, w1);
+            v[1] = cmul_conj(buf[pad(j + St)], w1);
+            v[2] = cmul_conj(buf[pad(j + 2 * St)], w2);
+            v[3] = cmul_conj(buf[pad(j + 3 * St)], w3);
+            v[4] = cmul_conj(buf[pad(j + 4 * St)], w4);
+            v[5] = cmul_conj(buf[pad(j + 5 * St)], w5);
+            dft6<true>(v);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) store_out(j + q * St, v[q]);
         }
     }
 }

@@ -230,7 +230,7 @@ static int vfft_run(const VfftGeom& g, const float* dem, int64_t ld_in, float* n
     const dim3 tgrid(N / 32, N / 32, planes), kgrid(N / 32, N / 32, 1);
     f.dst = X;
     TOPO_LAUNCH("valley_fft_fwd", s, (vfft_fwd_kernel<N, VSRC_DEM><<<dim3(N, planes), S::NT, S::SMEM, s>>>(f)));
-    TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N));
+    TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(X, Y, N, N));
     TOPO_LAUNCH("valley_fft_fwd", s, (fft2d_fwd_cplx_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(Y, dhat, tw)));
 
     VfftInvParams q{};
@@ -245,13 +245,13 @@ static int vfft_run(const VfftGeom& g, const float* dem, int64_t ld_in, float* n
         // K^ of the pair
         f.kp = kp, f.dst = K1;
         TOPO_LAUNCH("valley_fft_fwd", s, (vfft_fwd_kernel<N, VSRC_KERN><<<dim3(N, 1), S::NT, S::SMEM, s>>>(f)));
-        TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N));
+        TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<kgrid, dim3(32, 8), 0, s>>>(K1, K2, N, N));
         TOPO_LAUNCH("valley_fft_fwd", s, (fft2d_fwd_cplx_kernel<N, true><<<dim3(N, 1), S::NT, S::SMEM, s>>>(K2, K1, tw)));
         // all tiles: D^ * K^ -> inverse along the rows' axis -> transpose -> inverse + fold
         // (only the window rows the fold pass uses travel through the first pass's stores and the transpose)
         const int ct0 = (g.HT + g.HB) / 32, ct1 = ceil_div(g.HT + g.HB + g.V_y, 32);
         TOPO_LAUNCH("valley_fft_inv", s, (fft2d_inv_product_kernel<N><<<dim3(planes, N), S::NT, S::SMEM, s>>>(dhat, K1, X, tw, ct0 * 32, ct1 * 32)));
-        TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<dim3(ct1 - ct0, N / 32, planes), dim3(32, 8), 0, s>>>(X, Y, N, ct0));
+        TOPO_LAUNCH("valley_fft_transpose", s, fft2d_transpose_kernel<<<dim3(ct1 - ct0, N / 32, planes), dim3(32, 8), 0, s>>>(X, Y, N, N, ct0));
         q.a = Y, q.angle_a = kp.angle_a, q.angle_b = kp.angle_b, q.has_b = kp.kb != nullptr;
         TOPO_LAUNCH("valley_fft_fold", s, (vfft_fold_kernel<N><<<dim3(N, planes), S::NT, S::SMEM, s>>>(q)));
     }
