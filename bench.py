@@ -364,7 +364,9 @@ def run_gpu(args, rank, world, local_rank):
 
     # N > 1: thin bands make the ~360 launches of a step latency-visible, so the static kernel sequence is captured in
     # a CUDA graph (halo exchange over NCCL and the statistics all-reduce stay outside it, every step)
-    graph = bands.SweepGraph() if (world > 1 and not args.no_graph) else None
+    # (N = 1 too: the kernels of a step sum to the same time either way, but eager launches leave up to 10 ms of host-side
+    # gaps per step on a slow host -- measured 163.8 vs 174.4 ms on two boxes with identical kernel times)
+    graph = bands.SweepGraph() if not args.no_graph else None
 
     def step():
         if graph is not None:
@@ -377,6 +379,9 @@ def run_gpu(args, rank, world, local_rank):
     launches0 = _lib.launch_count()
     ms_step, clocks = timed_steps(step, 0, args.steps, clocks_index=local_rank)
     launches = _lib.launch_count() - launches0 + (graph.launches * args.steps if graph is not None else 0)
+    used_graph = graph is not None
+    graph = None  # (frees the graph's memory pool: tens of GB of workspaces on one GPU)
+    torch.cuda.empty_cache()
     value = n_calls * ny * nx / (ms_step * 1e-3) / 1e6
 
     # ---- per-kernel attribution of one more step (CUDA events around every launch, on its stream)
@@ -472,7 +477,10 @@ def run_gpu(args, rank, world, local_rank):
     # ---------------- extra: the same sweep on the integer-valued DEM -------------------------------------
     if not args.no_extra:
         core_i = torch.from_numpy(make_dem_rows(ny, nx, ctx.r0, ctx.r1, integer=True)).to(device)
-        ms_i, _ = timed_steps(lambda: bands.sweep(core_i, ctx, sizes, sigmas, res_x, res_y), 2, max(2, min(args.steps, 3)))
+        graph_i = bands.SweepGraph() if used_graph else None
+        ms_i, _ = timed_steps((lambda: graph_i.run(core_i, ctx, sizes, sigmas, res_x, res_y)) if graph_i is not None else
+                              (lambda: bands.sweep(core_i, ctx, sizes, sigmas, res_x, res_y)), 2, max(2, min(args.steps, 3)))
+        graph_i = None
         extra["sweep_integer_dem"] = {
             "config": workload_config(ny, nx, sizes, "integer"), "ms_per_step": round(ms_i, 3),
             "value": round(n_calls * ny * nx / (ms_i * 1e-3) / 1e6, 1), "unit": "Mpixel/s",
@@ -655,7 +663,7 @@ def run_gpu(args, rank, world, local_rank):
         "dtype": "f32 in/out; u32 fixed-point + i64 sums (tpi/std), f64 accumulate (gaussian)", "data": "synthetic",
         "config": dict(workload_config(ny, nx, sizes, "float"),
                        parallelism=f"row bands x{world}, halo exchange over NVLink", numa_bound=bool(numa_bound),
-                       launch="CUDA graph replay of the sweep's kernel sequence" if graph is not None else "eager"),
+                       launch="CUDA graph replay of the sweep's kernel sequence" if used_graph else "eager"),
         "clocks": clocks.summary(),
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": e2e_h2d,
                 "d2h_bytes_per_step": e2e_d2h, "steps": e2e_steps, "band_rows": e2e_rows, "d2h_GBps_all_ranks_at_once": d2h_rates,
@@ -756,7 +764,7 @@ def main():
     ap.add_argument("--size", type=int, default=16384, help="DEM edge in pixels (default: config 4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extra", action="store_true", help="skip the integer-DEM / config 3 / config 5 extras")
-    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the sweep eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="launch the sweep eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
