@@ -40,11 +40,13 @@ typedef struct topo_view {
     int out_rows; /* rows to compute */
 } topo_view;
 
-/* Prefix planes shared by the tpi / std calls of ONE DEM band at several sizes (a multi-scale sweep): the
- * planes (trunc(z) - tmin, its centred square, and for float DEMs the fraction / the quantised elevation with
- * the fixed-point scale of max_size) do not depend on the disc size, so they are built by the first call that
- * needs them and reused by the later ones -- together with the column-prefix, summed-area and diagonal tables
- * of the octagon walk.  The caller owns `mem` (DEVICE, 256-byte aligned,
+/* Planes shared by the tpi / std calls of ONE DEM band at several sizes (a multi-scale sweep): the integer planes
+ * (trunc(z) - tmin, its centred square, and for float DEMs the fraction / the quantised elevation with the
+ * fixed-point scale of max_size) do not depend on the disc size, so they are built by the first call that needs them
+ * and reused by the later ones.  When max_size takes the FFT route (the default from size 128) what is kept is the
+ * float64 SPECTRUM of the tiled planes (one slot per plane pair) plus the mask spectrum of the size in flight;
+ * otherwise the prefix planes with the column-prefix, summed-area and diagonal tables of the octagon walk.
+ * The caller owns `mem` (DEVICE, 256-byte aligned,
  * >= topo_disc_cache_bytes(v, max_size, all_integer, zmin, zmax)), starts with valid = 0 and passes the same struct, DEM,
  * view, all_integer flag and range to every call; the input band must cover the halo of max_size.
  * NULL (or mem = NULL) = no sharing. */
@@ -54,7 +56,8 @@ typedef struct topo_disc_cache {
     int max_size; /* the planes are laid out for discs up to this size */
     int valid;    /* in/out: bits 2k / 2k+1 = row prefix / column-side tables of plane kind k
                      (0 trunc(z) - tmin, 1 its square (or the low 16 bits of a split square), 2 fraction,
-                     3 quantised elevation; the high half of a split square takes the next free kind) */
+                     3 quantised elevation; the high half of a split square takes the next free kind);
+                     bits 16 / 17: the spectrum of plane pair 0 / 1 (FFT route) */
     int mask_size; /* in/out, FFT route: the disc size whose mask spectrum sits behind the plane spectra (tpi(size) and
                       std(size) of a pair build it once); start with 0 */
 } topo_disc_cache;
